@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""Benchmark of the CV hot path (BASELINE.json metric: frames/s for C0/C_tau + projection + KMeans).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (config.workload = "C2"): synthetic 1M frames x 1,000 features per GPU, TICA lag 10,
+dim 4, KMeans(k=100) with fixed initial centroids and a fixed number of Lloyd iterations in the
+4-D CV space.  One "step" = one pass of the whole hot path over the resident matrix:
+column statistics -> fused standardise + C0/C_tau -> F x F eigenproblem -> projection (+ CV
+min/max, normalisation) -> KMeans.  N > 1: weak scaling, every rank owns a 1M-frame shard of one
+N*1M-frame series (lag halo exchanged, partial sums all-reduced every step).
+
+`value`   : frames/s with the matrix resident in HBM (device-timed, max over ranks).
+`e2e`     : frames/s through the public calculator API (TICACalculator + kmeans_lloyd) from pinned
+            HOST memory, H2D of the matrix and D2H of the results inside the timed region.
+`roofline`: the covariance kernel (dominant), timed live with CUDA events on its stream.
+`cpu_baseline` / `--impl reference`: the reference's CPU path (oracle/reference_path.py, "port")
+            on a bounded sample, all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+F = 1000
+N_PER_GPU = 1_000_000
+LAG = 10
+DIM = 4
+K = 100
+KM_ITERS = 10
+CPU_SAMPLE_FRAMES = 200_000
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--engine", default=os.environ.get("DCG_COV_ENGINE", "tc_3xtf32"))
+    ap.add_argument("--frames", type=int, default=N_PER_GPU, help="frames per GPU (default = C2)")
+    ap.add_argument("--features", type=int, default=F)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [p.strip() for p in r.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU path on the host cores
+# ----------------------------------------------------------------------------------------------
+def host_sample(frames: int, features: int):
+    """The first `frames` rows of the synthetic series, generated on the host."""
+    import numpy as np
+    import torch
+    from deep_cartograph_b200.synthetic import feature_matrix
+    return feature_matrix(max(frames, 1), features, 0, frames, torch.device("cpu")).numpy()
+
+
+def time_reference(frames: int, features: int, steps: int, warmup: int):
+    from oracle.reference_path import cpu_threads, run_reference_pipeline
+    X0 = host_sample(frames, features)
+    times = []
+    last = None
+    for i in range(warmup + steps):
+        X = X0.copy()
+        t0 = time.perf_counter()
+        last = run_reference_pipeline(X, LAG, DIM, K, KM_ITERS)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    mean_s = sum(times) / len(times)
+    return {"value": frames / mean_s, "unit": "frames/s", "cores": cpu_threads(), "kind": "port",
+            "sample": f"first {frames} frames x {features} features of the C2 series, lag {LAG}, d {DIM}, "
+                      f"KMeans k={K} x {KM_ITERS} iters; stages(s)=" +
+                      json.dumps({k: round(v, 4) for k, v in last["timings"].items()})}, mean_s
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, args.steps), max(0, min(args.warmup, 1))
+    cb, mean_s = time_reference(CPU_SAMPLE_FRAMES, args.features, steps, warmup)
+    line = {"impl": "reference", "metric": "frames/s, TICA C0/Ctau + projection + KMeans (hot path)",
+            "value": cb["value"], "unit": "frames/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+            "ms_per_step": mean_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, args.gpus, "cpu"),
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world, engine):
+    return {"workload": "C2: synthetic 1M frames x 1,000 features per GPU, TICA lag 10, dim 4, "
+                        f"KMeans k={K} x {KM_ITERS} Lloyd iterations (fixed init = first k projected frames)",
+            "frames_per_gpu": args.frames, "features": args.features, "lag": LAG, "dim": DIM,
+            "kmeans_k": K, "kmeans_iters": KM_ITERS, "cov_engine": engine,
+            "parallelism": f"frame-sharded x{world}", "l2": "inputs (4 GB/GPU) larger than L2, no flush needed"}
+
+
+# ----------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from deep_cartograph_b200 import linalg, ops
+    from deep_cartograph_b200.modules.cv_learning.cv_calculator import TICACalculator
+    from deep_cartograph_b200.modules.statistics import statistics
+    from deep_cartograph_b200.parallel import FrameShards
+    from deep_cartograph_b200.synthetic import feature_matrix
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    shards = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        shards = FrameShards()
+    n, f = args.frames, args.features
+    engine = args.engine
+    peaks = measured_peaks()
+
+    # ---- data: this rank's shard of one world*n-frame series, with room for the lag halo
+    buf = torch.empty((n + LAG, f), dtype=torch.float32, device=dev)
+    buf[:n] = feature_matrix(world * n, f, rank * n, (rank + 1) * n, dev)
+    X = buf[:n]
+    torch.cuda.synchronize()
+
+    cov_ev = []
+
+    def step(record=False):
+        st = ops.column_stats(X)
+        if shards is not None:
+            st = shards.merge_stats(st)
+        ntot = st["n"]
+        mean = st["mean"].to(torch.float32)
+        rng = torch.sqrt(st["m2"] / (ntot - 1)).to(torch.float32)
+        rng = torch.where(rng.abs() < 1e-8, torch.ones_like(rng), rng)
+        Xh = shards.with_halo(X, LAG) if shards is not None else X
+        if record:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        s = ops.lagged_covariance(Xh, LAG, mean, rng, engine=engine)
+        if record:
+            e1.record()
+            cov_ev.append((e0, e1))
+        if shards is not None:
+            s = shards.allreduce_sums(s)
+        evals, V = linalg.tica_from_sums(ops.symmetrize_upper(s["S0"]), s["St"], s["a"], s["b"], s["M"], DIM)
+        W = V.to(torch.float32)
+        P, pmin, pmax = ops.project(X, W, mean, rng)
+        if shards is not None:
+            pmin, pmax = shards.allreduce_minmax(pmin, pmax)
+        ops.standardize_(P, (pmax + pmin) / 2, (pmax - pmin) / 2)
+        # KMeans: fixed init = first K projected frames of rank 0, fixed number of Lloyd iterations
+        C = P[:K].to(torch.float64).clone()
+        if shards is not None:
+            shards.broadcast_(C, 0)
+        labels = torch.full((n,), -1, dtype=torch.int32, device=dev)
+        for _ in range(KM_ITERS):
+            r = ops.kmeans_step(P, C, labels)
+            sums, counts = r["sums"], r["counts"]
+            if shards is not None:
+                packed = shards.allreduce_sum_(torch.cat([sums.reshape(-1), counts]))
+                sums, counts = packed[:K * DIM].view(K, DIM), packed[K * DIM:]
+            nz = counts > 0
+            C = torch.where(nz[:, None], sums / counts.clamp(min=1.0)[:, None], C)
+        return evals, labels
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if shards is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ops.KERNEL_LAUNCHES
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        evals, labels = step(record=True)
+    t1.record()
+    sync_all()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ops.KERNEL_LAUNCHES - launches0
+    ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+    cov_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in cov_ev) / len(cov_ev)], dtype=torch.float64, device=dev)
+    if shards is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cov_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms.item()) / args.steps
+    value = world * n / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (covariance contraction)
+    M = n - LAG if world == 1 else n            # pairs per rank (last rank has n - lag)
+    alg_flops = 3.0 * f * f * M                  # 2F^2 (C_tau) + F^2 (upper C0) per pair
+    tf32_peak = peaks["bf16_tflops"] / 2.0       # dense TF32 = 1/2 of dense bf16 on the tcgen05 pipe
+    cov_s = float(cov_ms.item()) * 1e-3
+    achieved = alg_flops / cov_s / 1e12
+    issued_mult = {"tc_3xtf32": 3.0, "tc_1xtf32": 1.0, "simt_f32": 1.0}[engine]
+    roofline = {"bound": "tensor", "kernel": f"cov_lag ({engine})", "achieved": achieved, "peak": tf32_peak,
+                "unit": "TFLOP/s", "frac": achieved / tf32_peak, "traffic": None,
+                "issued_tflops": achieved * issued_mult, "frac_issued": achieved * issued_mult / tf32_peak,
+                "kernel_ms": cov_s * 1e3, "share_of_step": cov_s * 1e3 / ms_per_step,
+                "peak_source": f"{peaks['source']} bf16 burst / 2 (TF32 : bf16 = 1 : 2 on tcgen05)",
+                "algorithmic": "3*F^2 FLOP per frame pair; issued = x3 for 3xTF32"}
+
+    # ---- e2e through the public API with host buffers
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty((n, f), dtype=torch.float32, pin_memory=True)
+        host.copy_(X)
+        cfg = {"dimension": DIM, "lag_time": LAG, "features_normalization": "mean_std",
+               "backend": {"cov_engine": engine}}
+        outdir = os.path.join(ROOT, "gpurun_out", f"bench_e2e_rank{rank}")
+        os.makedirs(outdir, exist_ok=True)
+
+        def e2e_step():
+            calc = TICACalculator(configuration=cfg, output_path=outdir)
+            calc.load_training_tensor(host, shards=shards)          # H2D of the whole matrix
+            calc.create_output_folders()
+            calc.compute_cv()
+            calc.set_labels()
+            Pn = calc.normalize_cv()
+            init = Pn[:K].to(torch.float64).clone()
+            if shards is not None:
+                shards.broadcast_(init, 0)
+            res = statistics.kmeans_lloyd(Pn, init, max_iter=KM_ITERS, tol=0.0, shards=shards)
+            lab = res["labels"].cpu()                                # D2H of the result
+            cen = res["centers"].cpu()
+            return lab, cen
+
+        e2e_step()
+        sync_all()
+        tt = time.perf_counter()
+        e2e_steps = max(1, min(args.steps, 3))
+        for _ in range(e2e_steps):
+            e2e_step()
+        sync_all()
+        el = torch.tensor([time.perf_counter() - tt], dtype=torch.float64, device=dev)
+        if shards is not None:
+            dist.all_reduce(el, op=dist.ReduceOp.MAX)
+        e2e_s = float(el.item()) / e2e_steps
+        e2e = {"value": world * n / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": world * n * f * 4,
+               "d2h_bytes_per_step": world * n * 4 + K * DIM * 8, "ms_per_step": e2e_s * 1e3,
+               "api": "TICACalculator.load_training_tensor/compute_cv/normalize_cv + statistics.kmeans_lloyd"}
+
+    if rank == 0:
+        cpu_baseline = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu_baseline, _ = time_reference(CPU_SAMPLE_FRAMES, f, 1, 0)
+        line = {"metric": "frames/s, TICA C0/Ctau + projection + KMeans (hot path)", "value": value,
+                "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32 (tf32x3 tensor contraction, f64 accumulation)" if engine == "tc_3xtf32" else "f32",
+                "data": "synthetic", "config": workload_config(args, world, engine),
+                "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
+                "clocks": clocks, "eigenvalues": [float(v) for v in evals.cpu().tolist()]}
+        print(json.dumps(line), flush=True)
+    if shards is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

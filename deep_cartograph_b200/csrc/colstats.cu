@@ -1,0 +1,205 @@
+// A2: single-pass per-feature statistics (mean, M2, min, max) of a row-major float32 matrix.
+// Replaces training_df.agg(['mean','std','min','max']) (reference cv_calculator.py:295-297).
+//
+// Layout: X[n][ld]; a warp reads 32*VEC consecutive floats of one row (fully coalesced), the
+// CTA's 8 warps take 8 different rows per step; a CTA owns a (row block) x (column strip) tile.
+// Per thread: FP32 Welford over <= kRowsPerCta/8 rows (well conditioned even when |mean| >> std),
+// merged across the CTA and across row blocks in FP64 with Chan's formula.
+// HBM-bound: 4*f bytes per frame, read once.
+#include "dcg_common.cuh"
+
+namespace dcg {
+
+constexpr int kStatWarps = 8;
+constexpr int kStatThreads = kStatWarps * 32;
+constexpr int kStatRowsPerCta = 1024;
+constexpr int kStatUnroll = 4;
+
+struct StatPartial {  // one per (row block, column)
+  double mean;
+  double m2;
+};
+
+template <int VEC>
+__device__ __forceinline__ void load_vec(const float* p, float (&v)[VEC]) {
+  if constexpr (VEC == 4) {
+    float4 t = ldg_stream4(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else if constexpr (VEC == 2) {
+    float2 t = ldg_stream2(p);
+    v[0] = t.x; v[1] = t.y;
+  } else {
+    v[0] = ldg_stream1(p);
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kStatThreads)
+colstats_partial_kernel(const float* __restrict__ X, int64_t n, int f, int64_t ld,
+                        StatPartial* __restrict__ part, float* __restrict__ pmin,
+                        float* __restrict__ pmax) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col0 = (blockIdx.x * 32 + lane) * VEC;            // first column of this thread
+  const int64_t row_begin = (int64_t)blockIdx.y * kStatRowsPerCta;
+  const int64_t row_end = min(n, row_begin + kStatRowsPerCta);
+  const bool active = col0 < f;                                // f % VEC == 0 guaranteed by host
+
+  float mean[VEC], m2[VEC], mn[VEC], mx[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) { mean[v] = 0.f; m2[v] = 0.f; mn[v] = INFINITY; mx[v] = -INFINITY; }
+  float cnt = 0.f;
+
+  if (active) {
+    const float* base = X + col0;
+    int64_t r = row_begin + warp;
+    // unrolled: kStatUnroll independent loads in flight per thread
+    for (; r + (int64_t)(kStatUnroll - 1) * kStatWarps < row_end; r += (int64_t)kStatUnroll * kStatWarps) {
+      float x[kStatUnroll][VEC];
+#pragma unroll
+      for (int u = 0; u < kStatUnroll; ++u) load_vec<VEC>(base + (r + (int64_t)u * kStatWarps) * ld, x[u]);
+#pragma unroll
+      for (int u = 0; u < kStatUnroll; ++u) {
+        cnt += 1.f;
+        const float inv = __frcp_rn(cnt);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          const float d = x[u][v] - mean[v];
+          mean[v] = fmaf(d, inv, mean[v]);
+          m2[v] = fmaf(d, x[u][v] - mean[v], m2[v]);
+          mn[v] = fminf(mn[v], x[u][v]);
+          mx[v] = fmaxf(mx[v], x[u][v]);
+        }
+      }
+    }
+    for (; r < row_end; r += kStatWarps) {
+      float x[VEC];
+      load_vec<VEC>(base + r * ld, x);
+      cnt += 1.f;
+      const float inv = __frcp_rn(cnt);
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        const float d = x[v] - mean[v];
+        mean[v] = fmaf(d, inv, mean[v]);
+        m2[v] = fmaf(d, x[v] - mean[v], m2[v]);
+        mn[v] = fminf(mn[v], x[v]);
+        mx[v] = fmaxf(mx[v], x[v]);
+      }
+    }
+  }
+
+  // CTA merge (FP64 Chan) of the 8 warps' partials, per column.
+  __shared__ double s_mean[kStatWarps][32 * VEC];
+  __shared__ double s_m2[kStatWarps][32 * VEC];
+  __shared__ float s_cnt[kStatWarps];
+  __shared__ float s_mn[kStatWarps][32 * VEC];
+  __shared__ float s_mx[kStatWarps][32 * VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    s_mean[warp][lane * VEC + v] = (double)mean[v];
+    s_m2[warp][lane * VEC + v] = (double)m2[v];
+    s_mn[warp][lane * VEC + v] = mn[v];
+    s_mx[warp][lane * VEC + v] = mx[v];
+  }
+  if (lane == 0) {
+    // rows handled by this warp (same for all its lanes)
+    int64_t rows = row_end - row_begin;
+    int64_t c = rows > warp ? (rows - warp + kStatWarps - 1) / kStatWarps : 0;
+    s_cnt[warp] = (float)c;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 32 * VEC; c += kStatThreads) {
+    const int col = blockIdx.x * 32 * VEC + c;
+    if (col >= f) continue;
+    double na = 0.0, ma = 0.0, qa = 0.0;
+    float lo = INFINITY, hi = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < kStatWarps; ++w) {
+      const double nb = (double)s_cnt[w];
+      if (nb > 0.0) {
+        const double mb = s_mean[w][c], qb = s_m2[w][c];
+        const double nt = na + nb, dl = mb - ma;
+        ma += dl * (nb / nt);
+        qa += qb + dl * dl * (na * nb / nt);
+        na = nt;
+        lo = fminf(lo, s_mn[w][c]);
+        hi = fmaxf(hi, s_mx[w][c]);
+      }
+    }
+    const size_t o = (size_t)blockIdx.y * f + col;
+    part[o].mean = ma;
+    part[o].m2 = qa;
+    pmin[o] = lo;
+    pmax[o] = hi;
+  }
+}
+
+// One thread per column: sequential Chan merge over row blocks (coalesced across columns).
+__global__ void colstats_merge_kernel(const StatPartial* __restrict__ part,
+                                      const float* __restrict__ pmin, const float* __restrict__ pmax,
+                                      int64_t n, int f, int row_blocks,
+                                      double* __restrict__ mean, double* __restrict__ m2,
+                                      float* __restrict__ minv, float* __restrict__ maxv) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= f) return;
+  double na = 0.0, ma = 0.0, qa = 0.0;
+  float lo = INFINITY, hi = -INFINITY;
+  for (int b = 0; b < row_blocks; ++b) {
+    const int64_t r0 = (int64_t)b * kStatRowsPerCta;
+    const double nb = (double)min((int64_t)kStatRowsPerCta, n - r0);
+    const StatPartial p = part[(size_t)b * f + col];
+    const double nt = na + nb, dl = p.mean - ma;
+    ma += dl * (nb / nt);
+    qa += p.m2 + dl * dl * (na * nb / nt);
+    na = nt;
+    lo = fminf(lo, pmin[(size_t)b * f + col]);
+    hi = fmaxf(hi, pmax[(size_t)b * f + col]);
+  }
+  mean[col] = ma;
+  m2[col] = qa;
+  minv[col] = lo;
+  maxv[col] = hi;
+}
+
+}  // namespace dcg
+
+using namespace dcg;
+
+extern "C" size_t dcg_colstats_workspace_bytes(int64_t n, int f) {
+  if (n <= 0 || f <= 0) return 0;
+  const size_t rb = (size_t)ceil_div(n, kStatRowsPerCta);
+  return align_up(rb * f * sizeof(StatPartial), 256) + 2 * align_up(rb * f * sizeof(float), 256);
+}
+
+extern "C" int dcg_colstats_f32(const float* X, int64_t n, int f, int64_t ld,
+                                double* mean, double* m2, float* minv, float* maxv,
+                                void* ws, size_t ws_bytes, void* stream) {
+  if (!X || !mean || !m2 || !minv || !maxv) return DCG_E_NULL;
+  if (n <= 0 || f <= 0 || ld < f) return DCG_E_SHAPE;
+  if (!ws || ws_bytes < dcg_colstats_workspace_bytes(n, f)) return DCG_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int rb = (int)ceil_div(n, kStatRowsPerCta);
+  if (rb > 65535) {
+    // grid.y limit: 65535 * 1024 rows = 67M frames per call; callers chunk beyond that
+    return DCG_E_SHAPE;
+  }
+  char* w = (char*)ws;
+  StatPartial* part = (StatPartial*)w;
+  w += align_up((size_t)rb * f * sizeof(StatPartial), 256);
+  float* pmin = (float*)w;
+  w += align_up((size_t)rb * f * sizeof(float), 256);
+  float* pmax = (float*)w;
+  int vec = row_vec_width(X, ld);
+  while (f % vec) vec >>= 1;
+  dim3 grid((unsigned)ceil_div(f, 32 * vec), (unsigned)rb);
+  if (vec == 4)
+    colstats_partial_kernel<4><<<grid, kStatThreads, 0, st>>>(X, n, f, ld, part, pmin, pmax);
+  else if (vec == 2)
+    colstats_partial_kernel<2><<<grid, kStatThreads, 0, st>>>(X, n, f, ld, part, pmin, pmax);
+  else
+    colstats_partial_kernel<1><<<grid, kStatThreads, 0, st>>>(X, n, f, ld, part, pmin, pmax);
+  DCG_LAUNCH_CHECK();
+  colstats_merge_kernel<<<(unsigned)ceil_div(f, 128), 128, 0, st>>>(part, pmin, pmax, n, f, rb,
+                                                                    mean, m2, minv, maxv);
+  DCG_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,336 @@
+// K1 / K3: KMeans E-step + M-step sums, and nearest-sample-to-centre, in the low-dimensional
+// CV space.  Replaces one sklearn lloyd_iter as triggered by statistics.kmeans_clustering
+// (reference modules/statistics/statistics.py:159-197; sklearn _k_means_lloyd.pyx:193-214) and
+// statistics.find_centroids (statistics.py:370-377).
+//
+// E-step arithmetic: every (frame, centre) score ||c||^2 - 2 y.c is SCREENED in FP32 on CUDA
+// cores (centres broadcast from shared memory, frames in registers).  A frame whose best and
+// second-best FP32 scores are closer than a rigorous rounding bound is RE-EVALUATED over all
+// centres in FP64 from the original data, so the label returned is always the FP64 argmin with
+// lowest-index tie-break -- identical to a float64 evaluation -- at FP32 speed.
+// M-step: FP64 sums / counts, privatised per CTA in shared memory when k*(d+1) fits, flushed
+// with FP64 atomics.
+//
+// Roofline: 4*d (or 8*d) bytes read + 4 bytes written per frame, 2*k*d FLOPs: HBM-bound for
+// k <~ 24, FP32-FMA-bound beyond (k=1000, d=10 is 500 FLOP/B).
+#include "dcg_common.cuh"
+
+namespace dcg {
+
+constexpr int kKmThreads = 512;
+constexpr int kKmR = 2;                       // frames per thread
+constexpr int kKmTile = kKmThreads * kKmR;
+constexpr size_t kKmSmemBudget = 200 * 1024;
+
+struct KmSmemPlan {
+  size_t centers_off, csq_off, acc_off, total;
+  int smem_acc;
+};
+
+static KmSmemPlan km_plan(int d, int dp, int k) {
+  KmSmemPlan p;
+  p.centers_off = 0;
+  p.csq_off = (size_t)k * dp * sizeof(float);
+  size_t o = align_up(p.csq_off + (size_t)k * sizeof(float), 16);
+  p.acc_off = o;
+  const size_t acc_bytes = (size_t)k * (d + 1) * sizeof(double);
+  p.smem_acc = (o + acc_bytes <= kKmSmemBudget) ? 1 : 0;
+  p.total = o + (p.smem_acc ? acc_bytes : 0);
+  return p;
+}
+
+// FP64 re-evaluation of one frame over all centres (rare path).
+template <typename T>
+__device__ __noinline__ void km_refine(const T* __restrict__ y, int d, const double* __restrict__ centers,
+                                       int k, int& lab, double& best, double& second) {
+  double yy[32];
+  for (int q = 0; q < d; ++q) yy[q] = (double)y[q];
+  best = INFINITY; second = INFINITY; lab = 0;
+  for (int j = 0; j < k; ++j) {
+    const double* c = centers + (size_t)j * d;
+    double dot = 0.0, csq = 0.0;
+    for (int q = 0; q < d; ++q) { const double cq = c[q]; dot = fma(yy[q], cq, dot); csq = fma(cq, cq, csq); }
+    const double s = csq - 2.0 * dot;
+    if (s < best) { second = best; best = s; lab = j; }
+    else if (s < second) second = s;
+  }
+}
+
+template <typename T, int DP>
+__global__ void __launch_bounds__(kKmThreads, 1)
+kmeans_step_kernel(const T* __restrict__ Y, int64_t n, int d, int64_t ld,
+                   const double* __restrict__ centers, int k, int32_t* __restrict__ labels,
+                   double* __restrict__ sums, double* __restrict__ counts, double* __restrict__ stats,
+                   T* __restrict__ gap, int update_sums, KmSmemPlan plan) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  float* c_s = reinterpret_cast<float*>(smem + plan.centers_off);
+  float* csq_s = reinterpret_cast<float*>(smem + plan.csq_off);
+  double* acc_s = reinterpret_cast<double*>(smem + plan.acc_off);
+  __shared__ float s_cmax2;
+
+  const int tid = threadIdx.x;
+  for (int i = tid; i < k * DP; i += kKmThreads) {
+    const int j = i / DP, q = i - j * DP;
+    c_s[i] = (q < d) ? (float)centers[(size_t)j * d + q] : 0.f;
+  }
+  if (tid == 0) s_cmax2 = 0.f;
+  __syncthreads();
+  for (int j = tid; j < k; j += kKmThreads) {
+    double s = 0.0;
+    for (int q = 0; q < d; ++q) { const double c = centers[(size_t)j * d + q]; s = fma(c, c, s); }
+    csq_s[j] = (float)s;
+    atomicMax(reinterpret_cast<int*>(&s_cmax2), __float_as_int((float)s));  // s >= 0: int order == float order
+  }
+  if (plan.smem_acc && update_sums)
+    for (int i = tid; i < k * (d + 1); i += kKmThreads) acc_s[i] = 0.0;
+  __syncthreads();
+  const float cmax2 = s_cmax2 * 1.0001f + 1e-30f;
+  const float cmaxn = sqrtf(cmax2);
+  // |err(score_a) - err(score_b)| <= 2 u (2d+6) (cmax2 + |y| |c|max), u = 2^-24; x1.5 margin
+  const float eps_k = 1.5f * 1.1920929e-7f * (float)(2 * d + 6);
+
+  double t_inertia = 0.0;
+  unsigned int t_changed = 0, t_ties = 0;
+
+  const int64_t ntiles = (n + kKmTile - 1) / kKmTile;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    float x[kKmR][DP];
+    int64_t idx[kKmR];
+    float xsq[kKmR];
+#pragma unroll
+    for (int r = 0; r < kKmR; ++r) {
+      idx[r] = tile * kKmTile + (int64_t)r * kKmThreads + tid;
+      const T* yrow = Y + min(idx[r], n - 1) * ld;
+      xsq[r] = 0.f;
+#pragma unroll
+      for (int q = 0; q < DP; ++q) {
+        x[r][q] = (q < d) ? (float)yrow[q] : 0.f;
+        xsq[r] = fmaf(x[r][q], x[r][q], xsq[r]);
+      }
+    }
+    float best[kKmR], second[kKmR];
+    int lab[kKmR];
+#pragma unroll
+    for (int r = 0; r < kKmR; ++r) { best[r] = INFINITY; second[r] = INFINITY; lab[r] = 0; }
+
+#pragma unroll 2
+    for (int j = 0; j < k; ++j) {
+      float c[DP];
+#pragma unroll
+      for (int q4 = 0; q4 < DP / 4; ++q4) {
+        const float4 t = reinterpret_cast<const float4*>(c_s + (size_t)j * DP)[q4];
+        c[4 * q4] = t.x; c[4 * q4 + 1] = t.y; c[4 * q4 + 2] = t.z; c[4 * q4 + 3] = t.w;
+      }
+      const float csq = csq_s[j];
+#pragma unroll
+      for (int r = 0; r < kKmR; ++r) {
+        float dot = 0.f;
+#pragma unroll
+        for (int q = 0; q < DP; ++q) dot = fmaf(x[r][q], c[q], dot);
+        const float s = fmaf(-2.f, dot, csq);
+        second[r] = fminf(second[r], fmaxf(s, best[r]));
+        lab[r] = (s < best[r]) ? j : lab[r];
+        best[r] = fminf(best[r], s);
+      }
+    }
+
+#pragma unroll
+    for (int r = 0; r < kKmR; ++r) {
+      if (idx[r] >= n) continue;
+      const T* yrow = Y + idx[r] * ld;
+      double b = (double)best[r], s2 = (double)second[r];
+      int l = lab[r];
+      const float eps = eps_k * (cmax2 + sqrtf(xsq[r]) * cmaxn);
+      if (k > 1 && !(second[r] - best[r] > eps)) km_refine<T>(yrow, d, centers, k, l, b, s2);
+      const double g = s2 - b;
+      if (k > 1 && g <= 0.0) ++t_ties;
+      if (gap) gap[idx[r]] = (T)g;
+      if (labels[idx[r]] != l) { ++t_changed; labels[idx[r]] = l; }
+      t_inertia += fmax(b + (double)xsq[r], 0.0);
+      if (update_sums) {
+        double* a = plan.smem_acc ? (acc_s + (size_t)l * (d + 1)) : nullptr;
+        if (a) {
+          for (int q = 0; q < d; ++q) atomicAdd(a + q, (double)yrow[q]);
+          atomicAdd(a + d, 1.0);
+        } else {
+          for (int q = 0; q < d; ++q) atomicAdd(sums + (size_t)l * d + q, (double)yrow[q]);
+          atomicAdd(counts + l, 1.0);
+        }
+      }
+    }
+  }
+
+  // CTA-level stats
+  t_inertia = warp_sum(t_inertia);
+  t_changed = __reduce_add_sync(0xffffffffu, t_changed);
+  t_ties = __reduce_add_sync(0xffffffffu, t_ties);
+  if ((tid & 31) == 0) {
+    if (t_changed) atomicAdd(stats + 0, (double)t_changed);
+    atomicAdd(stats + 1, t_inertia);
+    if (t_ties) atomicAdd(stats + 2, (double)t_ties);
+  }
+  if (plan.smem_acc && update_sums) {
+    __syncthreads();
+    for (int i = tid; i < k * (d + 1); i += kKmThreads) {
+      const double v = acc_s[i];
+      if (v != 0.0) {
+        const int j = i / (d + 1), q = i - j * (d + 1);
+        if (q < d) atomicAdd(sums + (size_t)j * d + q, v);
+        else atomicAdd(counts + j, v);
+      }
+    }
+  }
+}
+
+// ---- K3 ----------------------------------------------------------------------------------------
+// thread <-> centre, frames of the CTA's tile broadcast from shared memory; FP64 throughout.
+constexpr int kNcThreads = 128;
+constexpr int kNcMaxTile = 1024;   // frames per CTA tile (fewer when d is large)
+
+static int nearest_tile_rows(int d) {
+  int rows = (int)((160 * 1024) / ((size_t)d * sizeof(double)));
+  rows = rows / 32 * 32;
+  return rows > kNcMaxTile ? kNcMaxTile : rows;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kNcThreads)
+nearest_partial_kernel(const T* __restrict__ Y, int64_t n, int d, int64_t ld, int tile_rows,
+                       const double* __restrict__ centers, int k,
+                       double* __restrict__ pdist, int64_t* __restrict__ pidx) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  double* y_s = reinterpret_cast<double*>(smem);   // [tile_rows][d]
+  const int j = blockIdx.x * kNcThreads + threadIdx.x;
+  const int64_t t0 = (int64_t)blockIdx.y * tile_rows;
+  const int rows = (int)min((int64_t)tile_rows, n - t0);
+  for (int i = threadIdx.x; i < rows * d; i += kNcThreads) {
+    const int r = i / d, q = i - r * d;
+    y_s[i] = (double)Y[(t0 + r) * ld + q];
+  }
+  __syncthreads();
+  if (j >= k) return;
+  double c[32];
+  for (int q = 0; q < d; ++q) c[q] = centers[(size_t)j * d + q];
+  // np.linalg.norm semantics: compare sqrt(sum sq); the sqrt is only taken when the squared
+  // distance is not clearly larger than the incumbent's (monotone => cannot win otherwise).
+  double best = INFINITY, guard = INFINITY;
+  int besti = 0;
+  for (int r = 0; r < rows; ++r) {
+    double s = 0.0;
+    for (int q = 0; q < d; ++q) { const double df = y_s[r * d + q] - c[q]; s = fma(df, df, s); }
+    if (s <= guard) {
+      const double rt = sqrt(s);
+      if (rt < best) { best = rt; besti = r; guard = s * (1.0 + 1e-15); }
+    }
+  }
+  pdist[(size_t)blockIdx.y * k + j] = best;
+  pidx[(size_t)blockIdx.y * k + j] = t0 + besti;
+}
+
+__global__ void nearest_merge_kernel(const double* __restrict__ pdist, const int64_t* __restrict__ pidx,
+                                     int ntiles, int k, int64_t* __restrict__ argmin) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= k) return;
+  double best = INFINITY;
+  int64_t bi = 0;
+  for (int t = 0; t < ntiles; ++t) {          // tiles in frame order: strict < keeps the first index
+    const double s = pdist[(size_t)t * k + j];
+    if (s < best) { best = s; bi = pidx[(size_t)t * k + j]; }
+  }
+  argmin[j] = bi;
+}
+
+template <typename T, int DP>
+static int launch_kmeans(const T* Y, int64_t n, int d, int64_t ld, const double* centers, int k,
+                         int32_t* labels, double* sums, double* counts, double* stats, T* gap,
+                         int update_sums, cudaStream_t st) {
+  const KmSmemPlan plan = km_plan(d, DP, k);
+  if (plan.total > kKmSmemBudget) return DCG_E_SHAPE;
+  auto kern = kmeans_step_kernel<T, DP>;
+  DCG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.total));
+  int per_sm = 1;
+  DCG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kKmThreads, plan.total));
+  if (per_sm < 1) per_sm = 1;
+  const int64_t ntiles = ceil_div(n, kKmTile);
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, (int64_t)kNumSMs * per_sm));
+  kern<<<grid, kKmThreads, plan.total, st>>>(Y, n, d, ld, centers, k, labels, sums, counts, stats,
+                                             gap, update_sums, plan);
+  DCG_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T>
+static int dispatch_kmeans(const T* Y, int64_t n, int d, int64_t ld, const double* centers, int k,
+                           int32_t* labels, double* sums, double* counts, double* stats, T* gap,
+                           int update_sums, cudaStream_t st) {
+#define DCG_KM(DPV) return launch_kmeans<T, DPV>(Y, n, d, ld, centers, k, labels, sums, counts, stats, gap, update_sums, st)
+  if (d <= 4) DCG_KM(4);
+  if (d <= 8) DCG_KM(8);
+  if (d <= 12) DCG_KM(12);
+  if (d <= 16) DCG_KM(16);
+  if (d <= 24) DCG_KM(24);
+  DCG_KM(32);
+#undef DCG_KM
+}
+
+}  // namespace dcg
+
+using namespace dcg;
+
+extern "C" size_t dcg_kmeans_workspace_bytes(int64_t, int, int, int) { return 256; }
+
+extern "C" int dcg_kmeans_step(const void* Y, int64_t n, int d, int64_t ld, int dtype_bytes,
+                               const double* centers, int k, int32_t* labels,
+                               double* sums, double* counts, double* stats, void* gap,
+                               int update_sums, void* ws, size_t ws_bytes, void* stream) {
+  (void)ws; (void)ws_bytes;
+  if (!Y || !centers || !labels || !stats) return DCG_E_NULL;
+  if (update_sums && (!sums || !counts)) return DCG_E_NULL;
+  if (n <= 0 || d < 1 || d > 32 || ld < d || k < 1) return DCG_E_SHAPE;
+  if (dtype_bytes != 4 && dtype_bytes != 8) return DCG_E_MODE;
+  cudaStream_t st = (cudaStream_t)stream;
+  DCG_CUDA_TRY(cudaMemsetAsync(stats, 0, 3 * sizeof(double), st));
+  if (update_sums) {
+    DCG_CUDA_TRY(cudaMemsetAsync(sums, 0, (size_t)k * d * sizeof(double), st));
+    DCG_CUDA_TRY(cudaMemsetAsync(counts, 0, (size_t)k * sizeof(double), st));
+  }
+  if (dtype_bytes == 4)
+    return dispatch_kmeans<float>((const float*)Y, n, d, ld, centers, k, labels, sums, counts, stats,
+                                  (float*)gap, update_sums, st);
+  return dispatch_kmeans<double>((const double*)Y, n, d, ld, centers, k, labels, sums, counts, stats,
+                                 (double*)gap, update_sums, st);
+}
+
+extern "C" size_t dcg_nearest_workspace_bytes(int64_t n, int d, int k) {
+  if (n <= 0 || k <= 0 || d < 1 || d > 32) return 0;
+  const size_t tiles = (size_t)ceil_div(n, nearest_tile_rows(d));
+  return align_up(tiles * k * sizeof(double), 256) + align_up(tiles * k * sizeof(int64_t), 256);
+}
+
+extern "C" int dcg_nearest_to_centers(const void* Y, int64_t n, int d, int64_t ld, int dtype_bytes,
+                                      const double* centers, int k, int64_t* argmin,
+                                      void* ws, size_t ws_bytes, void* stream) {
+  if (!Y || !centers || !argmin) return DCG_E_NULL;
+  if (n <= 0 || d < 1 || d > 32 || ld < d || k < 1) return DCG_E_SHAPE;
+  if (dtype_bytes != 4 && dtype_bytes != 8) return DCG_E_MODE;
+  if (!ws || ws_bytes < dcg_nearest_workspace_bytes(n, d, k)) return DCG_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int tr = nearest_tile_rows(d);
+  const int64_t tiles = ceil_div(n, tr);
+  if (tiles > 65535) return DCG_E_SHAPE;   // ~67M frames per call; callers chunk beyond that
+  double* pdist = (double*)ws;
+  int64_t* pidx = (int64_t*)((char*)ws + align_up((size_t)tiles * k * sizeof(double), 256));
+  dim3 grid((unsigned)ceil_div(k, kNcThreads), (unsigned)tiles);
+  const size_t smem = (size_t)tr * d * sizeof(double);
+  if (dtype_bytes == 4) {
+    DCG_CUDA_TRY(cudaFuncSetAttribute(nearest_partial_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nearest_partial_kernel<float><<<grid, kNcThreads, smem, st>>>((const float*)Y, n, d, ld, tr, centers, k, pdist, pidx);
+  } else {
+    DCG_CUDA_TRY(cudaFuncSetAttribute(nearest_partial_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nearest_partial_kernel<double><<<grid, kNcThreads, smem, st>>>((const double*)Y, n, d, ld, tr, centers, k, pdist, pidx);
+  }
+  DCG_LAUNCH_CHECK();
+  nearest_merge_kernel<<<(unsigned)ceil_div(k, 128), 128, 0, st>>>(pdist, pidx, (int)tiles, k, argmin);
+  DCG_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,513 @@
+"""CV calculators of the hot path: PCA, TICA, hTICA (linear) on the B200 kernels.
+
+Host-side mirror of the reference's ``modules/cv_learning/cv_calculator.py``: same class names,
+constructor / method protocol, attribute names, error behaviour and ``model.zip`` layout
+(``CVCalculator`` :23, ``LinearCalculator`` :749, ``PCACalculator`` :2174, ``TICACalculator``
+:2217, ``HTICACalculator`` :2269, ``cv_calculators_map`` :2952).  The arithmetic runs on the
+device through ``deep_cartograph_b200.ops``; nothing here falls back to the CPU.
+
+Differences a maintainer should know (all documented in DESIGN.md):
+  * ``training_data`` lives on the GPU and stays RAW; standardisation is fused into the
+    covariance and projection kernels (the reference standardises in place at load, :799-804).
+    ``standardized_training_data()`` returns the reference's tensor on demand.
+  * ``project_data`` does not mutate its input (the reference does, :953-956).
+  * ``load_training_tensor`` accepts an in-memory matrix (synthetic benchmarks, sharded runs).
+"""
+from __future__ import annotations
+
+import copy
+import json
+import logging
+import os
+import shutil
+from pathlib import Path
+from typing import Dict, List, Optional, Tuple, Union
+
+import numpy as np
+import pandas as pd
+import torch
+
+from ... import linalg, ops
+from ...parallel import FrameShards
+from ..common import unzip_files, zip_files
+from ..plumed.colvars import create_dataframe_from_files
+
+logger = logging.getLogger(__name__)
+
+
+def _device(configuration: Dict) -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("deep_cartograph_b200 needs a CUDA device (B200); there is no CPU fallback")
+    idx = (configuration.get("backend") or {}).get("device")
+    if idx is None:
+        idx = torch.cuda.current_device()
+    return torch.device("cuda", int(idx))
+
+
+class CVCalculator:
+    """Base class (reference cv_calculator.py:23-745, hot-path subset)."""
+
+    def __init__(self, configuration: Optional[Dict] = None, output_path: Optional[str] = None):
+        self.configuration: Dict = copy.deepcopy(configuration) if configuration is not None else {}
+        self.architecture_config: Dict = self.configuration.get("architecture", {})
+        self.training_reading_settings: Dict = self.configuration.get("input_colvars", {}) or {}
+        self.feats_norm_mode = self.configuration.get("features_normalization", None)
+        self.backend: Dict = self.configuration.get("backend") or {}
+
+        self.ref_topology_path: Optional[str] = None
+        self.training_data: Optional[torch.Tensor] = None      # CUDA, float32, RAW features
+        self.training_data_labels: Optional[np.ndarray] = None
+        self.projection_data_labels: Optional[np.ndarray] = None
+        self.shards: Optional[FrameShards] = None              # set for multi-GPU frame sharding
+
+        self.features_ref_labels: List[str] = []
+        self.features_stats: Dict[str, np.ndarray] = {}
+        self.features_norm_mean: Optional[np.ndarray] = None
+        self.features_norm_range: Optional[np.ndarray] = None
+        self.num_features: int = 0
+        self.num_frames: int = 0                                # global number of frames
+
+        self.cv = None
+        self.cv_dimension: int = self.configuration.get("dimension")
+        self.cv_labels: List[str] = []
+        self.cv_name: Optional[str] = None
+        self.cv_range: List[Tuple[float, float]] = []
+        self.eigenvalues: Optional[np.ndarray] = None
+
+        self.parent_output_path: Optional[str] = output_path
+        self.temp_model_path: Optional[str] = None
+        self._dev_norm: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
+
+    def __del__(self):
+        try:
+            if self.temp_model_path and os.path.exists(self.temp_model_path):
+                shutil.rmtree(self.temp_model_path)
+        except Exception:
+            pass
+
+    # ---- model.zip ------------------------------------------------------------------------
+    @classmethod
+    def load(cls, model_path: str, output_path: str):
+        """Factory: restore the right calculator from a ``model.zip`` (reference :92-149)."""
+        if not os.path.exists(model_path):
+            raise FileNotFoundError(f"Model file not found: {model_path}")
+        temp_model_path = os.path.join(output_path, "model")
+        unzip_files(model_path, output_path)
+        metadata_path = os.path.join(temp_model_path, "metadata.json")
+        cv_name = None
+        if os.path.exists(metadata_path):
+            with open(metadata_path) as fh:
+                cv_name = json.load(fh).get("cv_name")
+        if not cv_name:
+            raise ValueError("Could not determine the CV name from the model file.")
+        klass = cv_calculators_map.get(cv_name)
+        if not klass:
+            raise TypeError(f"Unknown CV calculator name: {cv_name}")
+        inst = klass(output_path=output_path)
+        inst._load_from_folder(temp_model_path)
+        inst.temp_model_path = temp_model_path
+        return inst
+
+    def _load_from_folder(self, folder_path: str):
+        with open(os.path.join(folder_path, "metadata.json")) as fh:
+            meta = json.load(fh)
+        self.cv_dimension = meta.get("cv_dimension")
+        self.cv_name = meta.get("cv_name")
+        self.set_labels()
+        self.model_output_folder = os.path.join(self.parent_output_path, self.cv_name, "model")
+        if os.path.exists(self.model_output_folder):
+            shutil.rmtree(self.model_output_folder)
+        shutil.copytree(folder_path, self.model_output_folder)
+        with open(os.path.join(self.model_output_folder, "features_labels.txt")) as fh:
+            self.features_ref_labels = fh.read().strip().split("\n")
+        self.num_features = len(self.features_ref_labels)
+        ref_top = os.path.join(self.model_output_folder, "ref_topology.pdb")
+        self.ref_topology_path = ref_top if os.path.exists(ref_top) else None
+
+    def create_output_folders(self):
+        self.output_path = Path(self.parent_output_path) / self.cv_name
+        self.output_path.mkdir(parents=True, exist_ok=True)
+        self.training_output_folder = self.output_path / "training"
+        self.training_output_folder.mkdir(parents=True, exist_ok=True)
+        self.model_output_folder = self.output_path / "model"
+        self.model_output_folder.mkdir(parents=True, exist_ok=True)
+
+    def save_model(self):
+        """Files common to all calculators (reference :436-452)."""
+        with open(os.path.join(self.model_output_folder, "metadata.json"), "w") as fh:
+            json.dump({"cv_name": self.cv_name, "cv_dimension": self.cv_dimension}, fh)
+        np.savetxt(os.path.join(self.model_output_folder, "features_labels.txt"),
+                   self.features_ref_labels, fmt="%s")
+        if self.ref_topology_path is not None and os.path.exists(self.ref_topology_path):
+            shutil.copyfile(self.ref_topology_path, os.path.join(self.model_output_folder, "ref_topology.pdb"))
+
+    # ---- data -----------------------------------------------------------------------------
+    def load_training_data(self, train_colvars_paths: List[str],
+                           train_topology_paths: Optional[List[str]] = None,
+                           ref_topology_path: Optional[str] = None,
+                           features_list: Optional[List[str]] = None):
+        """Colvars files -> device matrix + statistics (reference :248-300)."""
+        self.ref_topology_path = ref_topology_path
+        if train_topology_paths is not None and self.ref_topology_path is None:
+            self.ref_topology_path = train_topology_paths[0]
+        logger.info("Reading training data from colvars files...")
+        df = create_dataframe_from_files(colvars_paths=train_colvars_paths,
+                                         topology_paths=train_topology_paths,
+                                         reference_topology=self.ref_topology_path,
+                                         features_list=features_list, file_label="traj_label",
+                                         **self.training_reading_settings)
+        labels = df.pop("traj_label").to_numpy()
+        X = torch.from_numpy(np.ascontiguousarray(df.to_numpy(dtype=np.float32)))
+        self.load_training_tensor(X, df.columns.tolist(), labels)
+
+    def load_training_tensor(self, X: torch.Tensor, features_labels: Optional[List[str]] = None,
+                             traj_labels: Optional[np.ndarray] = None,
+                             shards: Optional[FrameShards] = None):
+        """In-memory entry point: ``X`` is this rank's (frames x features) float32 shard
+        (CPU or CUDA).  With ``shards`` the statistics are merged across ranks and the lag
+        halo is exchanged later."""
+        dev = _device(self.configuration)
+        if X.dtype != torch.float32:
+            X = X.to(torch.float32)
+        lag = int(self.configuration.get("lag_time") or 0)
+        if shards is not None and lag > 0:
+            # spare rows after the shard so the lag halo is received in place (no second copy)
+            buf = torch.empty((X.shape[0] + lag, X.shape[1]), dtype=torch.float32, device=dev)
+            buf[:X.shape[0]].copy_(X, non_blocking=True)
+            self.training_data = buf[:X.shape[0]]
+        else:
+            self.training_data = X.to(dev, non_blocking=True).contiguous()
+        self.shards = shards
+        self.training_data_labels = traj_labels
+        n, f = self.training_data.shape
+        self.features_ref_labels = list(features_labels) if features_labels is not None else [f"f{i}" for i in range(f)]
+        self.num_features = f
+        logger.info(f"Number of features: {self.num_features}")
+
+        st = ops.column_stats(self.training_data)
+        if shards is not None:
+            st = shards.merge_stats(st)
+        self.num_frames = int(st["n"])
+        nn = self.num_frames
+        std = torch.sqrt(st["m2"] / (nn - 1)) if nn > 1 else torch.full_like(st["m2"], float("nan"))
+        # the reference's statistics are float32 (pandas on float32 columns)
+        self.features_stats = {
+            "mean": st["mean"].to(torch.float32).cpu().numpy(),
+            "std": std.to(torch.float32).cpu().numpy(),
+            "min": st["min"].cpu().numpy(),
+            "max": st["max"].cpu().numpy(),
+        }
+        self.features_norm_mean, self.features_norm_range = self.prepare_normalization()
+        self._dev_norm = None
+
+    def prepare_normalization(self) -> Tuple[np.ndarray, np.ndarray]:
+        """(mean, range) per normalisation mode; |range| < 1e-8 -> 1 (reference :308-363)."""
+        s = self.features_stats
+        if self.feats_norm_mode is None:
+            means = np.zeros(len(s["mean"]))
+            ranges = np.ones(len(s["mean"]))
+        elif self.feats_norm_mode == "mean_std":
+            means, ranges = s["mean"], s["std"]
+        elif self.feats_norm_mode == "min_max_range1":
+            means, ranges = s["min"], s["max"] - s["min"]
+        elif self.feats_norm_mode == "min_max_range2":
+            means, ranges = (s["min"] + s["max"]) / 2, (s["max"] - s["min"]) / 2
+        else:
+            logger.error(f"Normalization mode {self.feats_norm_mode} not recognized. Exiting...")
+            raise ValueError(f"Normalization mode {self.feats_norm_mode} not recognized.")
+        ranges = np.array(ranges, copy=True)
+        small = np.abs(ranges) < 1e-8
+        for i in np.flatnonzero(small):
+            logger.warning(f"Range for feature {i} is close to zero. Setting it to 1.0.")
+        ranges[small] = 1.0
+        return np.array(means, copy=True), ranges
+
+    def _norm_on_device(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        if self.features_norm_mean is None or self.features_norm_range is None:
+            raise ValueError("Feature normalization parameters have not been computed. Cannot normalize data.")
+        if self._dev_norm is None:
+            dev = self.training_data.device if self.training_data is not None else _device(self.configuration)
+            self._dev_norm = (torch.tensor(self.features_norm_mean, dtype=torch.float32, device=dev),
+                              torch.tensor(self.features_norm_range, dtype=torch.float32, device=dev))
+        return self._dev_norm
+
+    def standardized_training_data(self) -> torch.Tensor:
+        """The tensor the reference holds in ``training_data`` after load (:799-804)."""
+        m, r = self._norm_on_device()
+        return ops.standardize_(self.training_data.clone(), m, r)
+
+    def cv_ready(self) -> bool:
+        return self.cv is not None
+
+    # ---- main flow (reference :366-414) ------------------------------------------------------
+    def run(self, cv_dimension: Union[int, None] = None) -> Union[pd.DataFrame, None]:
+        if self.training_data is None:
+            logger.error("Training data not loaded. Cannot compute CV.")
+            return None
+        self.create_output_folders()
+        if cv_dimension:
+            self.cv_dimension = cv_dimension
+        self.compute_cv()
+        self.set_labels()
+        projection_df = None
+        if self.cv is not None:
+            projection = self.normalize_cv()          # one fused pass gives P and its min/max
+            self.save_model()
+            projection_df = pd.DataFrame(projection.cpu().numpy(), columns=self.cv_labels)
+        return projection_df
+
+    def compute_cv(self):
+        raise NotImplementedError
+
+    def set_labels(self):
+        self.cv_labels = [f"{cv_components_map[self.cv_name]} {i + 1}" for i in range(self.cv_dimension)]
+
+    def get_labels(self) -> List[str]:
+        return self.cv_labels
+
+    def get_cv_dimension(self) -> int:
+        return self.cv_dimension
+
+    def get_range(self):
+        return self.cv_range
+
+    def project_colvars(self, colvars_paths: Union[List[str], str],
+                        topology_paths: Union[List[str], str, None] = None) -> Union[pd.DataFrame, None]:
+        """Colvars file(s) -> projected DataFrame (reference :478-526)."""
+        df = create_dataframe_from_files(colvars_paths=colvars_paths, topology_paths=topology_paths,
+                                         reference_topology=self.ref_topology_path,
+                                         features_list=self.features_ref_labels, file_label="traj_label")
+        self.projection_data_labels = df.pop("traj_label").to_numpy()
+        X = torch.from_numpy(np.ascontiguousarray(df.to_numpy(dtype=np.float32)))
+        P = self.project_data(X)
+        return pd.DataFrame(P.cpu().numpy(), columns=self.cv_labels)
+
+
+class LinearCalculator(CVCalculator):
+    """Linear CVs: weights F x d + feature / CV normalisation (reference :749-1047)."""
+
+    def __init__(self, configuration: Optional[Dict] = None, output_path: Optional[str] = None):
+        super().__init__(configuration, output_path)
+        self.cv: Optional[np.ndarray] = None
+        self.weights_path: Optional[str] = None
+        self.cv_stats: Dict[str, np.ndarray] = {}
+        self.cv_norm_mean: Optional[np.ndarray] = None
+        self.cv_norm_range: Optional[np.ndarray] = None
+
+    def _load_from_folder(self, folder_path: str):
+        super()._load_from_folder(folder_path)
+        f = self.model_output_folder
+        self.cv = np.load(os.path.join(f, "cv_weights.npy"))
+        self.cv_norm_mean = np.load(os.path.join(f, "cv_norm_mean.npy"))
+        self.cv_norm_range = np.load(os.path.join(f, "cv_norm_range.npy"))
+        self.features_norm_mean = np.load(os.path.join(f, "features_norm_mean.npy"))
+        self.features_norm_range = np.load(os.path.join(f, "features_norm_range.npy"))
+
+    def normalize_data(self, data: torch.Tensor, normalizing_mean: torch.Tensor,
+                       normalizing_range: torch.Tensor) -> torch.Tensor:
+        """In-place ``(data - mean) / range`` on the device (reference :806-837)."""
+        dev = data.device if data.is_cuda else _device(self.configuration)
+        out = data if data.is_cuda else data.to(dev)
+        ops.standardize_(out, normalizing_mean.to(dev, torch.float32), normalizing_range.to(dev, torch.float32))
+        if not data.is_cuda:
+            data.copy_(out.cpu())
+        return data
+
+    def save_weights(self, weights_path: str):
+        np.save(weights_path, self.cv)
+
+    def save_model(self):
+        """model.zip with the reference's member names and float32 dtypes (:853-892)."""
+        super().save_model()
+        if self.cv is None:
+            raise ValueError("No Linear CV weights to save. Please compute the CV before saving the model.")
+        if self.cv_norm_mean is None or self.cv_norm_range is None:
+            raise ValueError("CV normalization parameters have not been computed. Cannot save model.")
+        if self.features_norm_mean is None or self.features_norm_range is None:
+            raise ValueError("Features normalization parameters have not been computed. Cannot save model.")
+        f = self.model_output_folder
+        self.save_weights(os.path.join(f, "cv_weights.npy"))
+        np.save(os.path.join(f, "cv_norm_mean.npy"), self.cv_norm_mean)
+        np.save(os.path.join(f, "cv_norm_range.npy"), self.cv_norm_range)
+        np.save(os.path.join(f, "features_norm_mean.npy"), self.features_norm_mean)
+        np.save(os.path.join(f, "features_norm_range.npy"), self.features_norm_range)
+        model_path = os.path.join(self.output_path, "model.zip")
+        zip_files(model_path, str(f))
+        shutil.rmtree(f)
+        logger.info(f"Model saved to {model_path}")
+
+    def get_cv_parameters(self) -> Dict:
+        return {"cv_name": self.cv_name, "cv_dimension": self.cv_dimension,
+                "features_norm_mode": self.feats_norm_mode,
+                "features_norm_mean": self.features_norm_mean,
+                "features_norm_range": self.features_norm_range,
+                "cv_stats": self.cv_stats, "weights": self.cv}
+
+    def get_cv_type(self) -> str:
+        return "linear"
+
+    def _weights_on(self, dev) -> torch.Tensor:
+        return torch.tensor(np.asarray(self.cv), dtype=torch.float32, device=dev)
+
+    def project_data(self, data: torch.Tensor, normalize_data: bool = True) -> torch.Tensor:
+        """Project onto the normalised CV space (reference :918-972): optional feature
+        standardisation, ``@ W``, then ``(P - cv_norm_mean) / cv_norm_range``.
+        Returns a tensor on the device of ``data``."""
+        if self.cv is None:
+            logger.error("CV has not been computed. Cannot project data.")
+            raise ValueError("CV has not been computed. Cannot project data.")
+        if normalize_data and (self.features_norm_mean is None or self.features_norm_range is None):
+            logger.error("Feature normalization parameters have not been computed. Cannot normalize data.")
+            raise ValueError("Feature normalization parameters have not been computed. Cannot normalize data.")
+        if self.cv_norm_mean is None or self.cv_norm_range is None:
+            logger.error("CV normalization parameters have not been computed. Cannot normalize projected data.")
+            raise ValueError("CV normalization parameters have not been computed. Cannot normalize projected data.")
+        dev = data.device if data.is_cuda else _device(self.configuration)
+        X = data.to(dev, torch.float32).contiguous()
+        mean = rng = None
+        if normalize_data:
+            mean = torch.tensor(self.features_norm_mean, dtype=torch.float32, device=dev)
+            rng = torch.tensor(self.features_norm_range, dtype=torch.float32, device=dev)
+        P, _, _ = ops.project(X, self._weights_on(dev), mean, rng, minmax=False)
+        ops.standardize_(P, torch.tensor(self.cv_norm_mean, dtype=torch.float32, device=dev),
+                         torch.tensor(self.cv_norm_range, dtype=torch.float32, device=dev))
+        return P if data.is_cuda else P.cpu()
+
+    def normalize_cv(self) -> torch.Tensor:
+        """CV min-max normalisation from the training projection (reference :974-991) and the
+        normalised training projection itself (reference run(), :403-406) from ONE fused pass
+        over the raw training data.  Returns the projected, normalised training shard."""
+        if self.training_data is None:
+            raise ValueError("Training data not loaded. Cannot compute CV statistics for normalization.")
+        dev = self.training_data.device
+        mean, rng = self._norm_on_device()
+        P, pmin, pmax = ops.project(self.training_data, self._weights_on(dev), mean, rng, minmax=True)
+        if self.shards is not None:
+            pmin, pmax = self.shards.allreduce_minmax(pmin, pmax)
+        mn = pmin.cpu().numpy()
+        mx = pmax.cpu().numpy()
+        self.cv_stats = {"min": mn, "max": mx}
+        self.cv_norm_mean = (mx + mn) / 2
+        self.cv_norm_range = (mx - mn) / 2
+        ops.standardize_(P, torch.tensor(self.cv_norm_mean, dtype=torch.float32, device=dev),
+                         torch.tensor(self.cv_norm_range, dtype=torch.float32, device=dev))
+        return P
+
+    # ---- shared by TICA / hTICA / PCA ---------------------------------------------------------
+    def _lagged_sums(self, lag: int, block: int = 0, want_st: bool = True) -> dict:
+        """Raw FP64 sums over the time-lagged pairs of this rank's shard (+ halo), summed over
+        ranks.  Pairs: x_t = Z[:N-lag], x_lag = Z[lag:] on the CONCATENATED series (files are
+        one time series, reference :278-300, 2247)."""
+        mean, rng = self._norm_on_device()
+        X = self.training_data
+        if self.shards is not None:
+            X = self.shards.with_halo(X, lag)
+        engine = self.backend.get("cov_engine")
+        s = ops.lagged_covariance(X, lag, mean, rng, block=block, engine=engine, want_st=want_st)
+        if self.shards is not None:
+            s = self.shards.allreduce_sums(s)
+        s["S0"] = ops.symmetrize_upper(s["S0"])
+        return s
+
+
+class PCACalculator(LinearCalculator):
+    """PCA (reference :2174-2215): sklearn ``PCA(n_components).fit`` == eigh of the covariance
+    of the standardised data; first weight of every component made non-negative."""
+
+    def __init__(self, configuration: Optional[Dict] = None, output_path: Optional[str] = None):
+        super().__init__(configuration, output_path)
+        self.cv_name = "pca"
+
+    def compute_cv(self):
+        if self.training_data is None:
+            logger.error("No training data available to compute PCA.")
+            return
+        s = self._lagged_sums(0, want_st=False)            # lag 0: plain Gram over all rows
+        evals, W = linalg.pca_from_sums(s["S0"], s["a"], s["M"], self.cv_dimension)
+        self.eigenvalues = evals.cpu().numpy()
+        self.cv = W.to(torch.float32).cpu().numpy()
+
+
+class TICACalculator(LinearCalculator):
+    """TICA (reference :2217-2267; mlcolvar TICA.compute with remove_average=True, reg 1e-6)."""
+
+    def __init__(self, configuration: Optional[Dict] = None, output_path: Optional[str] = None):
+        super().__init__(configuration, output_path)
+        self.cv_name = "tica"
+
+    def compute_cv(self):
+        lag = self.configuration.get("lag_time")
+        try:
+            s = self._lagged_sums(lag)
+            evals, V = linalg.tica_from_sums(s["S0"], s["St"], s["a"], s["b"], s["M"], self.cv_dimension)
+        except Exception as e:   # reference :2259-2264: log, leave self.cv unset
+            logger.error(f"TICA could not be computed. Error message: {e}")
+            return
+        self.eigenvalues = evals.cpu().numpy()
+        self.cv = V.to(torch.float32).cpu().numpy()
+
+
+class HTICACalculator(LinearCalculator):
+    """Hierarchical TICA (reference :2269-2384)."""
+
+    def __init__(self, configuration: Optional[Dict] = None, output_path: Optional[str] = None):
+        super().__init__(configuration, output_path)
+        self.cv_name = "htica"
+        self.num_subspaces = self.configuration.get("num_subspaces")
+        self.subspaces_dimension = self.configuration.get("subspaces_dimension")
+
+    def compute_cv(self):
+        lag = self.configuration.get("lag_time")
+        F = self.num_features
+        chunks = linalg.htica_chunks(F, self.num_subspaces)
+        if not chunks:
+            logger.error(f"Number of subspaces {self.num_subspaces} is larger than number of features {F}. Exiting...")
+            return
+        full_max = int(self.backend.get("htica_full_gram_max_features", 2048))
+        try:
+            if F <= full_max:
+                # one data pass: full Gram; level 2 = T1^T S T1 (exact)
+                s = self._lagged_sums(lag)
+                W, _, V2 = linalg.htica_from_full_sums(s["S0"], s["St"], s["a"], s["b"], s["M"],
+                                                       self.num_subspaces, self.subspaces_dimension,
+                                                       self.cv_dimension)
+            else:
+                # block-diagonal level 1 (1/num_subspaces of the MMA work), then a second pass
+                # over the level-1 projections for the small level-2 problem
+                width = F // self.num_subspaces
+                s = self._lagged_sums(lag, block=width)
+                T1 = linalg.htica_level1(s["S0"], s["St"], s["a"], s["b"], s["M"], chunks,
+                                         self.subspaces_dimension)
+                W = self._htica_level2(T1, lag)
+        except Exception as e:   # reference :2352-2357, 2376-2381
+            logger.error(f"TICA could not be computed. Error message: {e}")
+            return
+        self.cv = W.to(torch.float32).cpu().numpy()
+
+    def _htica_level2(self, T1: torch.Tensor, lag: int) -> torch.Tensor:
+        mean, rng = self._norm_on_device()
+        T1f = T1.to(torch.float32)
+        parts = []
+        for c0 in range(0, T1f.shape[1], 64):              # projection kernel: d <= 64 per call
+            Pc, _, _ = ops.project(self.training_data, T1f[:, c0:c0 + 64].contiguous(), mean, rng, minmax=False)
+            parts.append(Pc)
+        P = parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)
+        if self.shards is not None:
+            P = self.shards.with_halo(P, lag)
+        s = ops.lagged_covariance(P, lag, engine=self.backend.get("cov_engine"))
+        if self.shards is not None:
+            s = self.shards.allreduce_sums(s)
+        S0 = ops.symmetrize_upper(s["S0"])
+        _, V2 = linalg.tica_from_sums(S0, s["St"], s["a"], s["b"], s["M"], self.cv_dimension)
+        return T1 @ V2
+
+
+cv_calculators_map = {
+    "pca": PCACalculator,
+    "tica": TICACalculator,
+    "htica": HTICACalculator,
+}
+
+cv_names_map = {"pca": "PCA", "tica": "TICA", "htica": "HTICA", "deep_tica": "DeepTICA"}
+
+cv_components_map = {"pca": "PC", "tica": "TIC", "htica": "HTIC", "deep_tica": "DeepTIC"}

@@ -1,0 +1,288 @@
+"""Device operators of the CV hot path: thin torch-tensor wrappers over the C-ABI.
+
+Every operator takes CUDA tensors, launches on torch's current stream and returns CUDA
+tensors.  CPU tensors raise: the product has no CPU path (the CPU restatement lives in
+``oracle/`` and is test infrastructure only).
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import COV_ENGINES, DcgError  # noqa: F401
+
+
+# Number of libdcg_b200 kernels launched through this module (bench.py reports it).
+KERNEL_LAUNCHES = 0
+
+
+def _count(n: int) -> None:
+    global KERNEL_LAUNCHES
+    KERNEL_LAUNCHES += n
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(name: str, t: torch.Tensor, dtype=None) -> None:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: deep_cartograph_b200 has no CPU fallback")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+
+
+def _rows(name: str, t: torch.Tensor):
+    """(n, f, ld) of a 2-D tensor whose rows are contiguous."""
+    if t.dim() != 2:
+        raise ValueError(f"{name} must be 2-D (frames x features)")
+    if t.shape[1] > 1 and t.stride(1) != 1:
+        raise ValueError(f"{name} rows must be contiguous")
+    ld = t.stride(0) if t.shape[0] > 1 else t.shape[1]
+    return t.shape[0], t.shape[1], max(ld, t.shape[1])
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def default_cov_engine() -> int:
+    """Engine used when none is requested: env DCG_COV_ENGINE or the tcgen05 3xTF32 engine."""
+    name = os.environ.get("DCG_COV_ENGINE", "tc_3xtf32")
+    if name not in COV_ENGINES:
+        raise ValueError(f"DCG_COV_ENGINE={name!r}; choose from {sorted(COV_ENGINES)}")
+    return COV_ENGINES[name]
+
+
+def resolve_engine(engine) -> int:
+    if engine is None:
+        return default_cov_engine()
+    if isinstance(engine, str):
+        return COV_ENGINES[engine]
+    return int(engine)
+
+
+# ---- A2 ---------------------------------------------------------------------------------------
+def column_stats(X: torch.Tensor) -> dict:
+    """Single-pass per-feature statistics (reference cv_calculator.py:295-297).
+
+    Returns dict(n, mean[f64], m2[f64], min[f32], max[f32]); std(ddof=1) = sqrt(m2/(n-1))."""
+    _need_cuda("X", X, torch.float32)
+    n, f, ld = _rows("X", X)
+    lib = _lib.load()
+    dev = X.device
+    mean = torch.empty(f, dtype=torch.float64, device=dev)
+    m2 = torch.empty(f, dtype=torch.float64, device=dev)
+    mn = torch.empty(f, dtype=torch.float32, device=dev)
+    mx = torch.empty(f, dtype=torch.float32, device=dev)
+    max_rows = 65535 * 1024
+    if n <= max_rows:
+        ws = _ws(lib.dcg_colstats_workspace_bytes(n, f), dev)
+        _lib.call("dcg_colstats_f32", X.data_ptr(), n, f, ld, mean.data_ptr(), m2.data_ptr(),
+                  mn.data_ptr(), mx.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+        _count(2)
+        return {"n": n, "mean": mean, "m2": m2, "min": mn, "max": mx}
+    parts = [column_stats(X[s:s + max_rows]) for s in range(0, n, max_rows)]
+    return merge_column_stats(parts)
+
+
+def merge_column_stats(parts) -> dict:
+    """Chan merge of per-shard statistics (FP64); also used across GPUs."""
+    n = 0
+    mean = m2 = mn = mx = None
+    for p in parts:
+        if p["n"] == 0:
+            continue
+        if n == 0:
+            n, mean, m2, mn, mx = p["n"], p["mean"].clone(), p["m2"].clone(), p["min"].clone(), p["max"].clone()
+            continue
+        nb = p["n"]
+        nt = n + nb
+        dl = p["mean"] - mean
+        mean = mean + dl * (nb / nt)
+        m2 = m2 + p["m2"] + dl * dl * (n * nb / nt)
+        mn = torch.minimum(mn, p["min"])
+        mx = torch.maximum(mx, p["max"])
+        n = nt
+    return {"n": n, "mean": mean, "m2": m2, "min": mn, "max": mx}
+
+
+# ---- A4 ---------------------------------------------------------------------------------------
+def standardize_(X: torch.Tensor, mean: torch.Tensor, rng: torch.Tensor) -> torch.Tensor:
+    """In-place IEEE float32 ``(x - mean) / range`` (reference cv_calculator.py:806-837)."""
+    _need_cuda("X", X, torch.float32)
+    _need_cuda("mean", mean, torch.float32)
+    _need_cuda("range", rng, torch.float32)
+    n, f, ld = _rows("X", X)
+    if mean.numel() != f or rng.numel() != f:
+        raise ValueError("mean / range length must equal the number of columns")
+    if n == 0:
+        return X
+    _lib.call("dcg_standardize_f32", X.data_ptr(), n, f, ld, mean.contiguous().data_ptr(),
+              rng.contiguous().data_ptr(), _stream())
+    _count(1)
+    return X
+
+
+# ---- A5/A6/A7/A8 ------------------------------------------------------------------------------
+def lagged_covariance(X: torch.Tensor, lag: int, mean: Optional[torch.Tensor] = None,
+                      rng: Optional[torch.Tensor] = None, block: int = 0, engine=None,
+                      want_s0: bool = True, want_st: bool = True) -> dict:
+    """Raw FP64 sums over the M = n_rows - lag pairs of the (optionally standardised) rows:
+    S0 = sum z_t z_t^T (upper triangle valid), St = sum z_t z_{t+lag}^T, a = sum_{t<M} z_t,
+    b = sum_{t>=lag} z_t.  Replaces create_timelagged_dataset + TICA.compute's correlation
+    sums (reference cv_calculator.py:2244-2261)."""
+    _need_cuda("X", X, torch.float32)
+    n, f, ld = _rows("X", X)
+    if not (0 <= lag < n):
+        raise ValueError(f"lag {lag} out of range for {n} rows")
+    if (mean is None) != (rng is None):
+        raise ValueError("mean and range must be given together")
+    if mean is not None:
+        _need_cuda("mean", mean, torch.float32)
+        _need_cuda("range", rng, torch.float32)
+        mean = mean.contiguous()
+        rng = rng.contiguous()
+    eng = resolve_engine(engine)
+    lib = _lib.load()
+    dev = X.device
+    want_st = want_st and lag > 0
+    S0 = torch.empty((f, f), dtype=torch.float64, device=dev) if want_s0 else None
+    St = torch.empty((f, f), dtype=torch.float64, device=dev) if want_st else None
+    a = torch.empty(f, dtype=torch.float64, device=dev)
+    b = torch.empty(f, dtype=torch.float64, device=dev)
+    ws = _ws(lib.dcg_cov_workspace_bytes(n, f, lag, block, eng), dev)
+    _lib.call("dcg_cov_lag_f32", X.data_ptr(), n, f, ld, lag, _ptr(mean), _ptr(rng), block,
+              _ptr(S0), _ptr(St), a.data_ptr(), b.data_ptr(), eng, ws.data_ptr(), ws.numel(),
+              _stream())
+    _count(2 if eng == _lib.COV_SIMT_F32 else 3)      # colsum + engine (+ split reduction)
+    return {"S0": S0, "St": St, "a": a, "b": b, "M": n - lag}
+
+
+def symmetrize_upper(S: torch.Tensor) -> torch.Tensor:
+    """Full symmetric matrix from one whose upper triangle (incl. diagonal) is valid."""
+    U = torch.triu(S)
+    return U + torch.triu(S, 1).T
+
+
+# ---- A9/A10 -----------------------------------------------------------------------------------
+def project(X: torch.Tensor, W: torch.Tensor, mean: Optional[torch.Tensor] = None,
+            rng: Optional[torch.Tensor] = None, minmax: bool = True):
+    """``P = ((X - mean)/range) @ W`` in one pass, with per-column min / max of P.
+    Replaces LinearCalculator.normalize_cv / project_data (reference cv_calculator.py:918-991).
+    Returns (P, pmin, pmax)."""
+    _need_cuda("X", X, torch.float32)
+    _need_cuda("W", W, torch.float32)
+    n, f, ld = _rows("X", X)
+    if W.dim() != 2 or W.shape[0] != f:
+        raise ValueError(f"W must be ({f}, d)")
+    d = W.shape[1]
+    if not 1 <= d <= 64:
+        raise ValueError("1 <= d <= 64")
+    if (mean is None) != (rng is None):
+        raise ValueError("mean and range must be given together")
+    if mean is not None:
+        _need_cuda("mean", mean, torch.float32)
+        _need_cuda("range", rng, torch.float32)
+        mean = mean.contiguous()
+        rng = rng.contiguous()
+    lib = _lib.load()
+    dev = X.device
+    W = W.contiguous()
+    P = torch.empty((n, d), dtype=torch.float32, device=dev)
+    pmin = torch.empty(d, dtype=torch.float32, device=dev) if minmax else None
+    pmax = torch.empty(d, dtype=torch.float32, device=dev) if minmax else None
+    if n == 0:
+        return P, pmin, pmax
+    ws = _ws(lib.dcg_project_workspace_bytes(n, f, d), dev)
+    _lib.call("dcg_project_f32", X.data_ptr(), n, f, ld, _ptr(mean), _ptr(rng), W.data_ptr(), d,
+              P.data_ptr(), _ptr(pmin), _ptr(pmax), ws.data_ptr(), ws.numel(), _stream())
+    _count(2 * ((d + 15) // 16) + (1 if minmax else 0))
+    return P, pmin, pmax
+
+
+# ---- K1 / K3 ----------------------------------------------------------------------------------
+def _dtype_bytes(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return 4
+    if t.dtype == torch.float64:
+        return 8
+    raise TypeError(f"expected float32 or float64, got {t.dtype}")
+
+
+def kmeans_step(Y: torch.Tensor, centers: torch.Tensor, labels: torch.Tensor,
+                update_sums: bool = True, want_gap: bool = False) -> dict:
+    """One Lloyd E-step (+ M-step sums).  ``labels`` (int32) holds the previous labels and is
+    overwritten.  Returns dict(sums, counts, changed, inertia, ties, gap)."""
+    _need_cuda("Y", Y)
+    _need_cuda("centers", centers, torch.float64)
+    _need_cuda("labels", labels, torch.int32)
+    n, d, ld = _rows("Y", Y)
+    k = centers.shape[0]
+    if centers.dim() != 2 or centers.shape[1] != d:
+        raise ValueError("centers must be (k, d)")
+    if labels.numel() != n:
+        raise ValueError("labels must have one entry per frame")
+    dev = Y.device
+    centers = centers.contiguous()
+    sums = torch.empty((k, d), dtype=torch.float64, device=dev) if update_sums else None
+    counts = torch.empty(k, dtype=torch.float64, device=dev) if update_sums else None
+    stats = torch.empty(3, dtype=torch.float64, device=dev)
+    gap = torch.empty(n, dtype=Y.dtype, device=dev) if want_gap else None
+    ws = _ws(256, dev)
+    _lib.call("dcg_kmeans_step", Y.data_ptr(), n, d, ld, _dtype_bytes(Y), centers.data_ptr(), k,
+              labels.data_ptr(), _ptr(sums), _ptr(counts), stats.data_ptr(), _ptr(gap),
+              1 if update_sums else 0, ws.data_ptr(), ws.numel(), _stream())
+    _count(1)
+    return {"sums": sums, "counts": counts, "stats": stats, "gap": gap}
+
+
+def nearest_to_centers(Y: torch.Tensor, centers: torch.Tensor) -> torch.Tensor:
+    """Index of the first arg-min sample per centre (reference statistics.py:370-377)."""
+    _need_cuda("Y", Y)
+    _need_cuda("centers", centers, torch.float64)
+    n, d, ld = _rows("Y", Y)
+    k = centers.shape[0]
+    lib = _lib.load()
+    dev = Y.device
+    centers = centers.contiguous()
+    out = torch.empty(k, dtype=torch.int64, device=dev)
+    ws = _ws(lib.dcg_nearest_workspace_bytes(n, d, k), dev)
+    _lib.call("dcg_nearest_to_centers", Y.data_ptr(), n, d, ld, _dtype_bytes(Y), centers.data_ptr(),
+              k, out.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+    _count(2)
+    return out
+
+
+# ---- A11 --------------------------------------------------------------------------------------
+def ticacov_sums(f: torch.Tensor, g: torch.Tensor, w: Optional[torch.Tensor] = None,
+                 wl: Optional[torch.Tensor] = None) -> dict:
+    """Weighted raw correlation sums of DeepTICA network outputs (B x d, float32)."""
+    _need_cuda("f", f, torch.float32)
+    _need_cuda("g", g, torch.float32)
+    B, d = f.shape
+    f = f.contiguous()
+    g = g.contiguous()
+    lib = _lib.load()
+    n_out = lib.dcg_ticacov_out_doubles(d)
+    if n_out == 0:
+        raise ValueError("1 <= d <= 32")
+    out = torch.empty(n_out, dtype=torch.float64, device=f.device)
+    if w is not None:
+        w = w.to(torch.float32).contiguous()
+    if wl is not None:
+        wl = wl.to(torch.float32).contiguous()
+    _lib.call("dcg_ticacov_f32", f.data_ptr(), g.data_ptr(), _ptr(w), _ptr(wl), B, d,
+              out.data_ptr(), _stream())
+    _count(1)
+    o = 2 + d
+    return {"sw": out[0], "swl": out[1], "swf": out[2:o],
+            "sff": out[o:o + d * d].view(d, d), "sfg": out[o + d * d:o + 2 * d * d].view(d, d),
+            "slf": out[o + 2 * d * d:o + 2 * d * d + d], "slg": out[o + 2 * d * d + d:]}

@@ -1,0 +1,122 @@
+"""Frame sharding across the GPUs of one box.
+
+One process per GPU (``torchrun``); rank r owns the contiguous frame range
+``[r*N/G, (r+1)*N/G)``.  Every pass of the hot path is a sum / min / max over independent
+frames, so the data path needs exactly three exchanges, all issued through
+``torch.distributed`` (NCCL over NVLink on the GPUs, gloo in the CPU tests):
+
+  * statistics: all-gather of the per-rank (n, mean, M2, min, max) and a Chan merge (FP64);
+  * lag-tau halo: each rank receives the first ``lag`` rows of the next rank (the pairs (t, t+lag)
+    near a shard edge straddle it); the last rank has none;
+  * partial sums: one FP64 SUM all-reduce of ``[S0 | St | a | b | M]`` per covariance pass and of
+    ``[sums | counts | stats]`` per Lloyd iteration; min / max all-reduce of the CV range.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Rows ``[start, stop)`` owned by ``rank``."""
+    return (rank * n_total) // world, ((rank + 1) * n_total) // world
+
+
+class FrameShards:
+    """Collectives of the frame-sharded hot path for one process group."""
+
+    def __init__(self, group: Optional[dist.ProcessGroup] = None):
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised")
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+
+    # ---- statistics ---------------------------------------------------------------------------
+    def merge_stats(self, st: dict) -> dict:
+        """All-gather the per-rank column statistics and Chan-merge them in rank order."""
+        from .ops import merge_column_stats
+        f = st["mean"].numel()
+        dev = st["mean"].device
+        packed = torch.empty(1 + 4 * f, dtype=torch.float64, device=dev)
+        packed[0] = float(st["n"])
+        packed[1:1 + f] = st["mean"]
+        packed[1 + f:1 + 2 * f] = st["m2"]
+        packed[1 + 2 * f:1 + 3 * f] = st["min"].to(torch.float64)
+        packed[1 + 3 * f:] = st["max"].to(torch.float64)
+        out = [torch.empty_like(packed) for _ in range(self.world)]
+        dist.all_gather(out, packed, group=self.group)
+        parts = []
+        for p in out:
+            parts.append({"n": int(round(float(p[0].item()))), "mean": p[1:1 + f], "m2": p[1 + f:1 + 2 * f],
+                          "min": p[1 + 2 * f:1 + 3 * f].to(torch.float32),
+                          "max": p[1 + 3 * f:].to(torch.float32)})
+        return merge_column_stats(parts)
+
+    # ---- halo ---------------------------------------------------------------------------------
+    def with_halo(self, X: torch.Tensor, lag: int) -> torch.Tensor:
+        """Own rows followed by the first ``lag`` rows of the next rank (none on the last rank).
+        If ``X`` is a leading view of a buffer with ``lag`` spare rows, the halo is received in
+        place (no copy of the shard)."""
+        if lag == 0 or self.world == 1:
+            return X
+        n, f = X.shape
+        if n < lag:
+            raise ValueError(f"shard of {n} frames is shorter than the lag {lag}")
+        base = X._base if X._base is not None else None
+        room = (base is not None and base.dim() == 2 and base.shape[1] == f and base.is_contiguous()
+                and base.data_ptr() == X.data_ptr() and base.shape[0] >= n + lag)
+        has_next = self.rank + 1 < self.world
+        if has_next:
+            out = base[:n + lag] if room else torch.cat([X, torch.empty((lag, f), dtype=X.dtype, device=X.device)])
+            halo = out[n:n + lag]
+        else:
+            out = X
+            halo = None
+        head = X[:lag].contiguous()
+        ops = []
+        if self.rank > 0:
+            ops.append(dist.P2POp(dist.isend, head, self._global(self.rank - 1), group=self.group))
+        if has_next:
+            ops.append(dist.P2POp(dist.irecv, halo, self._global(self.rank + 1), group=self.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        return out
+
+    def _global(self, group_rank: int) -> int:
+        return dist.get_global_rank(self.group, group_rank) if self.group is not None else group_rank
+
+    # ---- reductions ---------------------------------------------------------------------------
+    def allreduce_sums(self, s: dict) -> dict:
+        """FP64 SUM all-reduce of one fused buffer [S0 | St | a | b | M]."""
+        keys = [k for k in ("S0", "St", "a", "b") if s.get(k) is not None]
+        dev = s["a"].device
+        flat = torch.cat([s[k].reshape(-1) for k in keys] +
+                         [torch.tensor([float(s["M"])], dtype=torch.float64, device=dev)])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+        out = dict(s)
+        o = 0
+        for k in keys:
+            nel = s[k].numel()
+            out[k] = flat[o:o + nel].view(s[k].shape)
+            o += nel
+        out["M"] = int(round(float(flat[o].item())))
+        return out
+
+    def allreduce_minmax(self, mn: torch.Tensor, mx: torch.Tensor):
+        mn = mn.clone()
+        mx = mx.clone()
+        dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=self.group)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=self.group)
+        return mn, mx
+
+    def allreduce_sum_(self, t: torch.Tensor) -> torch.Tensor:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def broadcast_(self, t: torch.Tensor, src: int = 0) -> torch.Tensor:
+        dist.broadcast(t, self._global(src), group=self.group)
+        return t

@@ -1,0 +1,136 @@
+/*
+ * dcg.h -- C-ABI of libdcg_b200.so: the B200 (sm_100a) kernels behind deep_cartograph's
+ * data-parallel collective-variable hot path.
+ *
+ * Conventions:
+ *   - plain C symbols, `int` return: 0 = ok, -1..-999 = -(cudaError_t), <= -1000 = argument errors
+ *     (see DCG_E_*); no exceptions, no stdout.
+ *   - every data pointer is a DEVICE pointer owned by the caller (e.g. torch tensor .data_ptr());
+ *     `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - calls are asynchronous with respect to `stream`; the caller synchronises before reading
+ *     results on the host;
+ *   - scratch memory is caller-provided: `ws` / `ws_bytes`, sized by the matching
+ *     *_workspace_bytes() query; the library keeps no mutable global state;
+ *   - no CPU fallback: without a CUDA device every compute entry point returns an error.
+ *
+ * Each entry point cites the reference interface (paths under /root/reference/deep_cartograph/)
+ * whose arithmetic it replaces.
+ */
+#ifndef DCG_H_
+#define DCG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCG_VERSION 100 /* 0.1.0 */
+
+/* argument errors */
+#define DCG_E_NULL      (-1000) /* required pointer is NULL */
+#define DCG_E_SHAPE     (-1001) /* n/f/d/k/lag/ld out of range */
+#define DCG_E_WORKSPACE (-1002) /* ws too small or NULL */
+#define DCG_E_ALIGN     (-1003) /* pointer alignment */
+#define DCG_E_ARCH      (-1004) /* device is not sm_100 (tensor-core path) */
+#define DCG_E_MODE      (-1005) /* unknown precision / mode flag */
+
+/* covariance contraction engines (dcg_cov_lag_f32 `engine`) */
+#define DCG_COV_SIMT_F32   0 /* CUDA-core FP32 FMA tiles, FP64 flush (validation engine)        */
+#define DCG_COV_TC_3XTF32  1 /* tcgen05 kind::tf32, split precision hi*hi + hi*lo + lo*hi       */
+#define DCG_COV_TC_1XTF32  2 /* tcgen05 kind::tf32, single pass (fast, ~1e-3 relative)          */
+
+int dcg_version(void);
+const char* dcg_error_string(int code);
+/* sm count / compute capability of the current device; returns 0 or an error */
+int dcg_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- A2: per-feature statistics -------------------------------------------------------------
+ * Replaces `training_df.agg(['mean','std','min','max'])`
+ * (modules/cv_learning/cv_calculator.py:295-297).  Single pass over X (n x f, row stride ld
+ * floats): per-thread FP32 Welford, FP64 Chan merge.  Outputs: mean[f], m2[f] (sum of squared
+ * deviations from the mean; std(ddof=1) = sqrt(m2/(n-1))), minv[f], maxv[f].                  */
+size_t dcg_colstats_workspace_bytes(int64_t n, int f);
+int dcg_colstats_f32(const float* X, int64_t n, int f, int64_t ld,
+                     double* mean, double* m2, float* minv, float* maxv,
+                     void* ws, size_t ws_bytes, void* stream);
+
+/* ---- A4: in-place standardisation ------------------------------------------------------------
+ * Replaces `LinearCalculator.normalize_data` (cv_calculator.py:806-837): x = (x - mean[j]) /
+ * range[j] with IEEE float32 subtraction and division.  Also used for the CV normalisation of
+ * projected data (cv_calculator.py:966-970) with f = d.                                        */
+int dcg_standardize_f32(float* X, int64_t n, int f, int64_t ld,
+                        const float* mean, const float* range, void* stream);
+
+/* ---- A5/A6/A7/A8: fused standardise + C0 / C_tau accumulation -------------------------------
+ * Replaces mlcolvar `create_timelagged_dataset` + `TICA.compute`'s correlation sums
+ * (cv_calculator.py:2244-2261, 2306-2378) and sklearn PCA's Gram (cv_calculator.py:2204-2210).
+ * With z_t = (x_t - mean)/range (mean/range NULL: X is used as is), rows t = 0..n_rows-1 and
+ * M = n_rows - lag pairs:
+ *     S0[i,j]   = sum_{t<M} z_t[i] z_t[j]        (upper triangle i<=j is valid; lower undefined)
+ *     St[i,j]   = sum_{t<M} z_t[i] z_{t+lag}[j]  (full, not symmetrised; NULL to skip; lag=0 skips)
+ *     colsum_t  = sum_{t<M} z_t ,  colsum_lag = sum_{t>=lag} z_t
+ * all FP64, row-major f x f.  `block` > 0 restricts both matrices to the diagonal blocks of that
+ * width (hTICA level 1, cv_calculator.py:2331-2354); entries outside are left untouched.
+ * For a frame shard, pass own rows + the `lag` halo rows of the next shard.
+ * Outputs are OVERWRITTEN (not accumulated).                                                    */
+size_t dcg_cov_workspace_bytes(int64_t n_rows, int f, int lag, int block, int engine);
+int dcg_cov_lag_f32(const float* X, int64_t n_rows, int f, int64_t ld, int lag,
+                    const float* mean, const float* range, int block,
+                    double* S0, double* St, double* colsum_t, double* colsum_lag,
+                    int engine, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- A9/A10: projection ----------------------------------------------------------------------
+ * Replaces `LinearCalculator.normalize_cv` + `project_data` (cv_calculator.py:918-991):
+ * P[t,:] = ((x_t - mean)/range) @ W  (mean/range NULL: no standardisation), W is f x d row-major
+ * float32, P is n x d row-major float32.  pmin/pmax (d, float32, may be NULL) receive the
+ * per-column min / max of P (for cv_norm_mean / cv_norm_range).  1 <= d <= 64.                  */
+size_t dcg_project_workspace_bytes(int64_t n, int f, int d);
+int dcg_project_f32(const float* X, int64_t n, int f, int64_t ld,
+                    const float* mean, const float* range,
+                    const float* W, int d, float* P, float* pmin, float* pmax,
+                    void* ws, size_t ws_bytes, void* stream);
+
+/* ---- K1: KMeans E-step + M-step sums ---------------------------------------------------------
+ * Replaces one sklearn `lloyd_iter` as triggered by `statistics.kmeans_clustering`
+ * (modules/statistics/statistics.py:159-197; sklearn/cluster/_k_means_lloyd.pyx:193-214):
+ * label = argmin_j ||c_j||^2 - 2 y.c_j, lowest index wins ties.  Y is n x d (row stride ld),
+ * `dtype_bytes` wide (4 = float32, 8 = float64); centers is k x d FP64 (the Lloyd driver owns the
+ * centres in FP64).  Scores are screened in FP32 and near-ties re-evaluated in FP64, so the label is
+ * the FP64 argmin.  labels (int32, n) is read (previous labels, -1 initially) and overwritten.  Outputs (overwritten): sums[k*d], counts[k] FP64;
+ * stats[0] = number of labels that changed, stats[1] = inertia sum ||y - c_label||^2,
+ * stats[2] = number of exact ties (FP64 second-best == best).  gap (n, may be NULL) receives
+ * second-best minus best score per frame in `dtype_bytes` precision.  Limits: 1 <= d <= 32,
+ * k*(pad4(d)+1)*4 bytes <= 200 KB (centres live in shared memory).
+ * update_sums = 0 skips sums/counts (final E-step, _kmeans.py:742-754).                         */
+size_t dcg_kmeans_workspace_bytes(int64_t n, int d, int k, int dtype_bytes);
+int dcg_kmeans_step(const void* Y, int64_t n, int d, int64_t ld, int dtype_bytes,
+                    const double* centers, int k, int32_t* labels,
+                    double* sums, double* counts, double* stats, void* gap,
+                    int update_sums, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- K3: nearest sample to each centre -------------------------------------------------------
+ * Replaces `statistics.find_centroids` (statistics.py:370-377): argmin_t ||y_t - c_j||_2 per
+ * centre j, first index on ties, evaluated in FP64.  argmin is int64[k].                        */
+size_t dcg_nearest_workspace_bytes(int64_t n, int d, int k);
+int dcg_nearest_to_centers(const void* Y, int64_t n, int d, int64_t ld, int dtype_bytes,
+                           const double* centers, int k, int64_t* argmin,
+                           void* ws, size_t ws_bytes, void* stream);
+
+/* ---- A11: DeepTICA minibatch covariance ------------------------------------------------------
+ * Replaces the correlation sums inside mlcolvar `DeepTICA.training_step` (driven from
+ * cv_calculator.py:1508-1524).  f, g are B x d float32 network outputs (row-major), w / wl the
+ * per-sample weights (NULL = 1).  Outputs FP64 raw sums (overwritten):
+ *   out[0]            = sum w,          out[1] = sum wl
+ *   out[2 .. 2+d)     = sum w f
+ *   then d*d each     : sum w f f^T,  sum wl f g^T,  then d each: sum wl f, sum wl g
+ * The caller forms mean-free C0 / C_tau in FP64 (see host code).  1 <= d <= 32.                 */
+size_t dcg_ticacov_out_doubles(int d);
+int dcg_ticacov_f32(const float* f, const float* g, const float* w, const float* wl,
+                    int64_t B, int d, double* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCG_H_ */

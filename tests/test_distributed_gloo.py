@@ -1,0 +1,108 @@
+"""world_size-2 gloo tests (CPU) of the frame-sharding collectives: statistics merge,
+lag halo, partial-sum all-reduce.  The per-rank kernels are emulated with the oracle so that only
+the host-side sharding logic is under test here; the device kernels are covered by -m gpu."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, n, f, lag, out):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import oracle
+        from conftest import synth_features
+        from deep_cartograph_b200 import linalg
+        from deep_cartograph_b200.parallel import FrameShards, shard_range
+        X = synth_features(n, f, seed=1)
+        s, e = shard_range(n, rank, world)
+        shards = FrameShards()
+        # ---- statistics: per-rank (n, mean, M2, min, max) -> Chan merge
+        loc = oracle.column_stats(X[s:e])
+        st = {"n": e - s, "mean": torch.from_numpy(loc["mean"]),
+              "m2": torch.from_numpy(loc["std"] ** 2 * (e - s - 1)),
+              "min": torch.from_numpy(loc["min"].astype(np.float32)),
+              "max": torch.from_numpy(loc["max"].astype(np.float32))}
+        merged = shards.merge_stats(st)
+        ref = oracle.column_stats(X)
+        assert merged["n"] == n
+        np.testing.assert_allclose(merged["mean"].numpy(), ref["mean"], rtol=1e-12)
+        np.testing.assert_allclose(np.sqrt(merged["m2"].numpy() / (n - 1)), ref["std"], rtol=1e-10)
+        np.testing.assert_array_equal(merged["min"].numpy(), ref["min"].astype(np.float32))
+        # ---- halo: received in place when the shard is a view of a buffer with spare rows
+        mean, rng = oracle.prepare_normalization(ref, "mean_std")
+        Z = oracle.standardize(X, mean, rng)
+        buf = torch.zeros((e - s + lag, f), dtype=torch.float32)
+        buf[:e - s] = torch.from_numpy(Z[s:e])
+        Zh = shards.with_halo(buf[:e - s], lag)
+        if rank + 1 < world:
+            assert Zh.shape[0] == e - s + lag and Zh.data_ptr() == buf.data_ptr()
+            np.testing.assert_array_equal(Zh[e - s:].numpy(), Z[e:e + lag])
+        else:
+            assert Zh.shape[0] == e - s
+        # copy path (no spare rows)
+        Zh2 = shards.with_halo(torch.from_numpy(Z[s:e].copy()), lag)
+        np.testing.assert_array_equal(Zh2.numpy(), Zh.numpy())
+        # ---- partial sums -> one fused FP64 all-reduce -> same TICA as the unsharded oracle
+        S0, St, a, b, M = oracle.lagged_sums(Zh.numpy(), lag)
+        tot = shards.allreduce_sums({"S0": torch.from_numpy(S0), "St": torch.from_numpy(St),
+                                     "a": torch.from_numpy(a), "b": torch.from_numpy(b), "M": M})
+        rS0, rSt, ra, rb, rM = oracle.lagged_sums(Z, lag)
+        assert tot["M"] == rM == n - lag
+        np.testing.assert_allclose(tot["S0"].numpy(), rS0, rtol=1e-11, atol=1e-8)
+        np.testing.assert_allclose(tot["St"].numpy(), rSt, rtol=1e-11, atol=1e-8)
+        evals, V = linalg.tica_from_sums(tot["S0"], tot["St"], tot["a"], tot["b"], tot["M"], 3)
+        revals, rV = oracle.tica(Z, lag, 3)
+        np.testing.assert_allclose(evals.numpy(), revals, rtol=1e-9)
+        np.testing.assert_allclose(V.numpy(), rV, atol=1e-8)
+        # ---- min / max and plain sums
+        mn, mx = shards.allreduce_minmax(torch.tensor([float(rank)]), torch.tensor([float(rank)]))
+        assert mn.item() == 0 and mx.item() == world - 1
+        t = shards.allreduce_sum_(torch.ones(3, dtype=torch.float64))
+        assert torch.all(t == world)
+        c = torch.full((2,), float(rank))
+        shards.broadcast_(c, 0)
+        assert torch.all(c == 0)
+        out.put((rank, "ok"))
+    except Exception as ex:  # noqa: BLE001
+        import traceback
+        out.put((rank, "FAIL: " + traceback.format_exc()))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("n,f,lag", [(600, 12, 7), (257, 5, 1)])
+def test_frame_sharding_world2(n, f, lag):
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 29500 + (os.getpid() + n) % 2000
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, f, lag, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(240)
+    results = [out.get(timeout=5) for _ in range(world)]
+    for p in procs:
+        assert p.exitcode == 0, results
+    assert sorted(r[1] for r in results) == ["ok"] * world, results
+
+
+def test_shard_range_partitions_all_frames():
+    from deep_cartograph_b200.parallel import shard_range
+    for n, w in [(10, 3), (1_000_000, 8), (7, 8)]:
+        rs = [shard_range(n, r, w) for r in range(w)]
+        assert rs[0][0] == 0 and rs[-1][1] == n
+        assert all(rs[i][1] == rs[i + 1][0] for i in range(w - 1))

@@ -1,0 +1,441 @@
+"""GPU parity tests: every CUDA entry point (through the C-ABI via ctypes) against the CPU
+oracle on the same seeded inputs, and the calculators / step APIs against the reference's golden
+artefacts (C1 fixture).  Run on the B200 box: ``pytest -m gpu``.
+
+Tolerances (BASELINE.json north_star): covariances / eigenvalues 1e-5 relative to float64
+(normwise), eigenvectors 1e-5 up to sign, projections 1e-4, KMeans labels identical from fixed
+initial centroids with exact-tie frames counted and reported.
+"""
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+import oracle
+from conftest import GOLDEN, synth_features
+
+pytestmark = pytest.mark.gpu
+
+ENGINES = ["simt_f32", "tc_3xtf32"]
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from deep_cartograph_b200 import _lib
+    _lib.load()            # fail loudly if the extension is missing
+    return torch.device("cuda:0")
+
+
+def _cuda(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+# ------------------------------------------------------------------------------------------------
+# A2 column statistics
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,f", [(164, 54), (1, 7), (5000, 1000), (3001, 4950 // 5), (777, 3),
+                                 (20000, 130), (1025, 128)])
+def test_colstats_matches_oracle(dev, n, f):
+    from deep_cartograph_b200 import ops
+    X = synth_features(n, f, seed=n + f)
+    st = ops.column_stats(_cuda(X, dev))
+    ref = oracle.column_stats(X)
+    assert st["n"] == n
+    np.testing.assert_allclose(st["mean"].cpu().numpy(), ref["mean"], rtol=2e-7, atol=1e-9)
+    if n > 1:
+        std = np.sqrt(st["m2"].cpu().numpy() / (n - 1))
+        np.testing.assert_allclose(std, ref["std"], rtol=3e-6)
+    assert np.array_equal(st["min"].cpu().numpy(), ref["min"].astype(np.float32))   # exact
+    assert np.array_equal(st["max"].cpu().numpy(), ref["max"].astype(np.float32))
+
+
+def test_colstats_strided_rows_and_golden(dev, c1):
+    from deep_cartograph_b200 import ops
+    X = c1["X"]
+    buf = torch.zeros((X.shape[0], 64), dtype=torch.float32, device=dev)
+    buf[:, :54] = _cuda(X, dev)
+    st = ops.column_stats(buf[:, :54])            # ld = 64 != f
+    std = torch.sqrt(st["m2"] / (X.shape[0] - 1)).to(torch.float32).cpu().numpy()
+    np.testing.assert_allclose(st["mean"].to(torch.float32).cpu().numpy(), c1["tica_features_norm_mean"], atol=2e-7)
+    np.testing.assert_allclose(std, c1["tica_features_norm_range"], rtol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------
+# A4 standardisation (bit-exact IEEE sub + div)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,f", [(164, 54), (4096, 1000), (1000, 4950 // 5), (513, 7), (10000, 4), (33, 2)])
+def test_standardize_is_bit_exact(dev, n, f):
+    from deep_cartograph_b200 import ops
+    X = synth_features(n, f, seed=3)
+    st = oracle.column_stats(X)
+    m, r = oracle.prepare_normalization(st, "mean_std")
+    ref = oracle.standardize(X, m, r)
+    Z = ops.standardize_(_cuda(X, dev), _cuda(m.astype(np.float32), dev), _cuda(r.astype(np.float32), dev))
+    got = Z.cpu().numpy()
+    mism = np.count_nonzero(got != ref)
+    assert mism == 0, f"{mism} of {got.size} elements differ from IEEE (x-m)/r"
+
+
+# ------------------------------------------------------------------------------------------------
+# A5/A6 covariance sums
+# ------------------------------------------------------------------------------------------------
+def _cov_case(dev, X, lag, engine, standardise=True, block=0):
+    from deep_cartograph_b200 import ops
+    st = oracle.column_stats(X)
+    m, r = oracle.prepare_normalization(st, "mean_std" if standardise else None)
+    Z = oracle.standardize(X, m, r) if standardise else X
+    mean = _cuda(m.astype(np.float32), dev) if standardise else None
+    rng = _cuda(r.astype(np.float32), dev) if standardise else None
+    s = ops.lagged_covariance(_cuda(X, dev), lag, mean, rng, block=block, engine=engine)
+    torch.cuda.synchronize()
+    if lag > 0:
+        S0, St, a, b, M = oracle.lagged_sums(Z, lag)
+    else:
+        Z64 = Z.astype(np.float64)
+        S0, St, a, b, M = Z64.T @ Z64, None, Z64.sum(0), Z64.sum(0), Z.shape[0]
+    return s, (S0, St, a, b, M)
+
+
+def _assert_cov_close(s, ref, tol, block=0):
+    S0, St, a, b, M = ref
+    F = S0.shape[0]
+    assert s["M"] == M
+    mask_u = np.triu(np.ones((F, F), dtype=bool))
+    mask_f = np.ones((F, F), dtype=bool)
+    if block:
+        blk = np.arange(F) // block
+        same = blk[:, None] == blk[None, :]
+        mask_u &= same
+        mask_f &= same
+    got0 = s["S0"].cpu().numpy()
+    scale0 = np.abs(S0).max()
+    assert np.abs(got0 - S0)[mask_u].max() <= tol * scale0, np.abs(got0 - S0)[mask_u].max() / scale0
+    if St is not None:
+        gott = s["St"].cpu().numpy()
+        scalet = np.abs(St).max()
+        assert np.abs(gott - St)[mask_f].max() <= tol * scalet, np.abs(gott - St)[mask_f].max() / scalet
+    np.testing.assert_allclose(s["a"].cpu().numpy(), a, rtol=1e-6, atol=1e-6 * M ** 0.5 + 1e-4)
+    np.testing.assert_allclose(s["b"].cpu().numpy(), b, rtol=1e-6, atol=1e-6 * M ** 0.5 + 1e-4)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("n,f,lag", [(164, 54, 1), (3000, 256, 10), (2500, 1000, 10), (999, 130, 7),
+                                     (4100, 495, 1), (600, 64, 33), (300, 5, 2), (2048, 384, 128)])
+def test_cov_sums_match_float64(dev, engine, n, f, lag):
+    X = synth_features(n, f, seed=n)
+    s, ref = _cov_case(dev, X, lag, engine)
+    _assert_cov_close(s, ref, 1e-5)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_cov_lag0_gram_and_unstandardised(dev, engine):
+    X = synth_features(1500, 200, seed=5)
+    s, ref = _cov_case(dev, X, 0, engine, standardise=True)
+    assert s["St"] is None
+    _assert_cov_close(s, ref, 1e-5)
+    Z = oracle.standardize(X, *oracle.prepare_normalization(oracle.column_stats(X), "mean_std"))
+    s, ref = _cov_case(dev, Z, 3, engine, standardise=False)
+    _assert_cov_close(s, ref, 1e-5)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_cov_block_diagonal_mode(dev, engine):
+    X = synth_features(2000, 990, seed=11)
+    s, ref = _cov_case(dev, X, 5, engine, block=99)
+    _assert_cov_close(s, ref, 1e-5, block=99)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_cov_linearity_over_frame_chunks(dev, engine):
+    """Size-independent property: sums over [0,n) == sums over two overlapping-by-lag halves."""
+    from deep_cartograph_b200 import ops
+    n, f, lag = 20000, 512, 10
+    X = _cuda(synth_features(n, f, seed=2), dev)
+    whole = ops.lagged_covariance(X, lag, engine=engine)
+    h = n // 2
+    first = ops.lagged_covariance(X[:h + lag], lag, engine=engine)    # own rows + halo
+    second = ops.lagged_covariance(X[h:], lag, engine=engine)
+    assert first["M"] + second["M"] == whole["M"]
+    for k in ("S0", "St"):
+        tot = torch.triu(first[k] + second[k]) if k == "S0" else first[k] + second[k]
+        ref = torch.triu(whole[k]) if k == "S0" else whole[k]
+        err = (tot - ref).abs().max().item() / ref.abs().max().item()
+        assert err < 2e-6, (k, err)
+
+
+# ------------------------------------------------------------------------------------------------
+# A9/A10 projection
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,f,d", [(164, 54, 2), (5000, 1000, 4), (1234, 990, 10), (4000, 130, 1),
+                                   (777, 64, 16), (900, 200, 50), (3, 7, 3)])
+def test_projection_matches_float64(dev, n, f, d):
+    from deep_cartograph_b200 import ops
+    X = synth_features(n, f, seed=d)
+    st = oracle.column_stats(X)
+    m, r = oracle.prepare_normalization(st, "mean_std")
+    rngW = np.random.default_rng(d)
+    W = (rngW.standard_normal((f, d)) / np.sqrt(f)).astype(np.float32)
+    Z = oracle.standardize(X, m, r)
+    ref = oracle.project(Z, W)
+    P, pmin, pmax = ops.project(_cuda(X, dev), _cuda(W, dev), _cuda(m.astype(np.float32), dev),
+                                _cuda(r.astype(np.float32), dev))
+    got = P.cpu().numpy()
+    np.testing.assert_allclose(got, ref, atol=1e-4 * max(1.0, np.abs(ref).max()))
+    assert np.array_equal(pmin.cpu().numpy(), got.min(axis=0))
+    assert np.array_equal(pmax.cpu().numpy(), got.max(axis=0))
+    P2, _, _ = ops.project(_cuda(Z, dev), _cuda(W, dev), minmax=False)
+    np.testing.assert_allclose(P2.cpu().numpy(), ref, atol=1e-4 * max(1.0, np.abs(ref).max()))
+
+
+# ------------------------------------------------------------------------------------------------
+# K1 KMeans
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("name", ["blobs_d2_k5", "blobs_d4_k10_grid", "blobs_d10_k40", "uniform_d3_k7_grid"])
+def test_kmeans_labels_identical_to_reference(dev, kmeans_ref, name, dtype):
+    """Labels from fixed initial centroids == the reference's statistics.cluster_data output;
+    any differing frame must be an exact / near tie, which is counted and reported."""
+    from deep_cartograph_b200.modules.statistics import statistics
+    X = kmeans_ref[f"{name}_X"].astype(dtype)
+    labels, centers = statistics.cluster_data(X, {"algorithm": "kmeans"}, kmeans_ref[f"{name}_init"])
+    ref_labels = kmeans_ref[f"{name}_labels"]
+    diff = np.flatnonzero(labels != ref_labels)
+    if dtype == np.float64:
+        res = oracle.kmeans_lloyd(X, kmeans_ref[f"{name}_init"])
+        gap = res["second"][diff] - res["best"][diff]
+        assert np.all(gap <= 1e-9), f"{len(diff)} labels differ and are not ties: {gap}"
+        if len(diff) == 0:
+            np.testing.assert_allclose(centers, kmeans_ref[f"{name}_centers"], rtol=1e-9, atol=1e-11)
+        assert statistics.last_kmeans_report["n_iter"] == res["n_iter"]
+    else:
+        # float32 inputs: compare with the oracle run on the same float32 values
+        res = oracle.kmeans_lloyd(X.astype(np.float64), kmeans_ref[f"{name}_init"])
+        d2 = np.flatnonzero(labels != res["labels"])
+        gap = res["second"][d2] - res["best"][d2]
+        assert np.all(gap <= 1e-6), f"{len(d2)} labels differ and are not near-ties: {gap}"
+
+
+def test_kmeans_step_counts_ties_and_gap(dev):
+    from deep_cartograph_b200 import ops
+    Y = np.array([[0.0, 0.0], [1.0, 0.0], [0.5, 0.0], [0.5, 1.0], [0.25, 0.0]])
+    C = np.array([[0.0, 0.0], [1.0, 0.0]])
+    for dt in (np.float64, np.float32):
+        lab = torch.full((5,), -1, dtype=torch.int32, device=dev)
+        res = ops.kmeans_step(_cuda(Y.astype(dt), dev), _cuda(C, dev), lab, want_gap=True)
+        assert lab.cpu().tolist() == [0, 1, 0, 0, 0]          # ties -> lowest index
+        st = res["stats"].cpu().numpy()
+        assert st[0] == 5 and st[2] == 2
+        np.testing.assert_allclose(res["counts"].cpu().numpy(), [4, 1])
+        np.testing.assert_allclose(res["sums"].cpu().numpy(), [[1.25, 1.0], [1.0, 0.0]])
+        np.testing.assert_allclose(res["gap"].cpu().numpy(), [1.0, 1.0, 0.0, 0.0, 0.5], atol=1e-6)
+        np.testing.assert_allclose(st[1], 0 + 0 + 0.25 + 1.25 + 0.0625, rtol=1e-6)
+
+
+def test_kmeans_large_k_against_oracle(dev):
+    rng = np.random.default_rng(0)
+    k, d, n = 1000, 10, 60000
+    cent = rng.uniform(-0.9, 0.9, size=(k, d))
+    Y = (cent[rng.integers(0, k, size=n)] + 0.03 * rng.standard_normal((n, d))).astype(np.float32)
+    init = Y[:k].astype(np.float64)
+    from deep_cartograph_b200 import ops
+    lab = torch.full((n,), -1, dtype=torch.int32, device=dev)
+    res = ops.kmeans_step(_cuda(Y, dev), _cuda(init, dev), lab, want_gap=True)
+    ref_lab, best, second = oracle.kmeans_assign(Y.astype(np.float64), init)
+    got = lab.cpu().numpy()
+    diff = np.flatnonzero(got != ref_lab)
+    assert np.all(second[diff] - best[diff] <= 1e-12), (len(diff), (second - best)[diff])
+    sums = np.zeros((k, d)); np.add.at(sums, ref_lab, Y.astype(np.float64))
+    if len(diff) == 0:
+        np.testing.assert_allclose(res["sums"].cpu().numpy(), sums, rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(res["counts"].cpu().numpy(), np.bincount(ref_lab, minlength=k))
+
+
+def test_kmeans_empty_cluster_relocation(dev):
+    from deep_cartograph_b200.modules.statistics import statistics
+    X = np.array([[0.0, 0.0], [0.1, 0.0], [5.0, 5.0], [5.1, 5.0], [9.0, 9.0]])
+    init = np.array([[0.0, 0.0], [5.0, 5.0], [100.0, 100.0]])
+    labels, centers = statistics.cluster_data(X, {"algorithm": "kmeans"}, init)
+    res = oracle.kmeans_lloyd(X, init)
+    assert np.array_equal(labels, res["labels"])
+    np.testing.assert_allclose(centers, res["centers"], rtol=1e-12)
+
+
+# ------------------------------------------------------------------------------------------------
+# K3 nearest sample to each centre
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cv", ["pca", "tica", "htica"])
+def test_find_centroids_matches_golden(dev, c1, cv):
+    from deep_cartograph_b200.modules.statistics import statistics
+    Y = c1[f"{cv}_cluster_cv"]
+    lab = c1[f"{cv}_cluster_label"]
+    cent = np.stack([Y[lab == k].mean(axis=0) for k in np.unique(lab)])
+    df = pd.DataFrame(Y, columns=["a", "b"])
+    out = statistics.find_centroids(df, cent, ["a", "b"])
+    assert np.array_equal(out["centroid"].to_numpy(), c1[f"{cv}_cluster_centroid"])
+
+
+def test_nearest_to_centers_ties_and_sizes(dev):
+    from deep_cartograph_b200 import ops
+    rng = np.random.default_rng(1)
+    Y = np.round(rng.uniform(-1, 1, size=(30000, 3)), 2)        # many duplicates -> ties
+    C = Y[rng.integers(0, len(Y), size=300)] + 0.0
+    got = ops.nearest_to_centers(_cuda(Y, dev), _cuda(C, dev)).cpu().numpy()
+    assert np.array_equal(got, oracle.find_centroids(Y, C))
+    got32 = ops.nearest_to_centers(_cuda(Y.astype(np.float32), dev), _cuda(C, dev)).cpu().numpy()
+    assert np.array_equal(got32, oracle.find_centroids(Y.astype(np.float32), C))
+
+
+# ------------------------------------------------------------------------------------------------
+# A11 DeepTICA covariance
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,d", [(256, 2), (4096, 3), (10000, 10), (513, 32)])
+def test_deeptica_loss_matches_oracle(dev, B, d):
+    from deep_cartograph_b200.modules.cv_learning.deep_tica import tica_covariances, tica_loss
+    rng = np.random.default_rng(B)
+    f = rng.standard_normal((B, d)).astype(np.float32)
+    g = (0.8 * f + 0.5 * rng.standard_normal((B, d))).astype(np.float32)
+    w = rng.uniform(0.5, 1.5, size=B).astype(np.float32)
+    C0, Ct = tica_covariances(_cuda(f, dev), _cuda(g, dev), _cuda(w, dev), _cuda(w, dev))
+    rC0, rCt, _ = oracle.deeptica_cov(f, g, w, w)
+    np.testing.assert_allclose(C0.cpu().numpy(), rC0, atol=1e-5 * np.abs(rC0).max())
+    np.testing.assert_allclose(Ct.cpu().numpy(), rCt, atol=1e-5 * np.abs(rCt).max())
+    loss, evals = tica_loss(_cuda(f, dev), _cuda(g, dev), reg=1e-6)
+    rloss, revals = oracle.deeptica_loss(f, g, reg=1e-6)
+    np.testing.assert_allclose(evals.detach().cpu().numpy(), revals, rtol=1e-4, atol=1e-5)
+    assert abs(loss.item() - rloss) <= 1e-4 * abs(rloss)
+
+
+def test_deeptica_loss_gradient_matches_torch_autograd(dev):
+    from deep_cartograph_b200.modules.cv_learning.deep_tica import tica_loss
+    torch.manual_seed(0)
+    B, d = 2048, 4
+    f = torch.randn(B, d, device=dev, requires_grad=True)
+    g0 = torch.randn(B, d, device=dev)
+    g = (0.7 * f.detach() + 0.4 * g0).requires_grad_(True)
+    loss, _ = tica_loss(f, g, reg=1e-6)
+    loss.backward()
+    # plain torch float64 evaluation of the same loss
+    f64 = f.detach().double().requires_grad_(True)
+    g64 = g.detach().double().requires_grad_(True)
+    mu = f64.mean(0)
+    a = f64 - mu; b = g64 - mu
+    C0 = a.T @ a / B
+    Ct = 0.5 * (a.T @ b + b.T @ a) / B
+    L = torch.linalg.cholesky(C0 + 1e-6 * torch.eye(d, dtype=torch.float64, device=dev))
+    Li = torch.linalg.inv(L)
+    ev = torch.linalg.eigvalsh(Li @ Ct @ Li.T)
+    ref = -(ev ** 2).sum()
+    ref.backward()
+    assert abs(loss.item() - ref.item()) < 1e-5 * abs(ref.item())
+    np.testing.assert_allclose(f.grad.cpu().numpy(), f64.grad.cpu().numpy(), atol=2e-6 * f64.grad.abs().max().item() + 1e-9)
+    np.testing.assert_allclose(g.grad.cpu().numpy(), g64.grad.cpu().numpy(), atol=2e-6 * g64.grad.abs().max().item() + 1e-9)
+
+
+# ------------------------------------------------------------------------------------------------
+# calculators and step APIs on the C1 fixture (reference golden artefacts)
+# ------------------------------------------------------------------------------------------------
+def _config(engine="tc_3xtf32"):
+    return {"cvs": ["pca", "tica", "htica"],
+            "common": {"dimension": 2, "lag_time": 1, "features_normalization": "mean_std",
+                       "num_subspaces": 10, "subspaces_dimension": 5,
+                       "input_colvars": {"start": 0, "stop": None, "stride": 1},
+                       "backend": {"cov_engine": engine}}}
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_train_colvars_step_api_reproduces_golden(dev, c1, tmp_path, engine):
+    """The reference's own test (tests/test_train_colvars.py:86-161) on the B200 backend."""
+    from deep_cartograph_b200.tools import train_colvars
+    feats = [l.strip() for l in open(os.path.join(GOLDEN, "peptide_c1_features.txt")) if l.strip()]
+    out = train_colvars(configuration=_config(engine),
+                        train_colvars_paths=[os.path.join(GOLDEN, "peptide_c1.dat")],
+                        trajectory_names=["CA_example"], features_list=feats,
+                        output_folder=str(tmp_path / "train_colvars"))
+    tol_w = {"pca": 5e-6, "tica": 3e-4, "htica": 2e-4}     # as pinned for the oracle (LAPACK noise)
+    for cv in ("pca", "tica", "htica"):
+        assert os.path.exists(out[cv]["model_path"])
+        df = pd.read_csv(out[cv]["traj_paths"][0])
+        assert list(df.columns) == list(c1[f"{cv}_csv_cols"])
+        # projections within 1e-4 (+ half a unit of the 4-decimal print) of the golden CSV;
+        # for tica/htica the ill-conditioned eigenproblem adds the weight tolerance
+        np.testing.assert_allclose(df.to_numpy(), c1[f"{cv}_csv"], atol=1.6e-4 if cv == "pca" else 2e-3)
+        from deep_cartograph_b200.modules.cv_learning import CVCalculator
+        calc = CVCalculator.load(out[cv]["model_path"], str(tmp_path / f"load_{cv}"))
+        assert calc.cv.dtype == np.float32 and calc.cv.shape == (54, 2)
+        np.testing.assert_allclose(calc.cv, c1[f"{cv}_cv_weights"], atol=tol_w[cv])
+        np.testing.assert_allclose(calc.features_norm_mean, c1[f"{cv}_features_norm_mean"], atol=2e-7)
+        np.testing.assert_allclose(calc.features_norm_range, c1[f"{cv}_features_norm_range"], rtol=1e-6)
+
+
+@pytest.mark.parametrize("cv", ["pca", "tica", "htica"])
+def test_projection_with_golden_weights_reproduces_golden_csv(dev, c1, tmp_path, cv):
+    """The reference's tests/test_traj_projection.py: golden model -> golden CSV (KAT for the
+    projection + normalisation kernels)."""
+    from deep_cartograph_b200.modules.cv_learning.cv_calculator import cv_calculators_map
+    calc = cv_calculators_map[cv](configuration=_config()["common"], output_path=str(tmp_path))
+    calc.cv = c1[f"{cv}_cv_weights"]
+    calc.cv_norm_mean = c1[f"{cv}_cv_norm_mean"]
+    calc.cv_norm_range = c1[f"{cv}_cv_norm_range"]
+    calc.features_norm_mean = c1[f"{cv}_features_norm_mean"]
+    calc.features_norm_range = c1[f"{cv}_features_norm_range"]
+    P = calc.project_data(torch.from_numpy(c1["X"].copy()), normalize_data=True).numpy()
+    got = np.array([[float("%.4f" % v) for v in row] for row in P])
+    assert np.count_nonzero(got != c1[f"{cv}_csv"]) <= 3
+    np.testing.assert_allclose(P, c1[f"{cv}_csv"], atol=1.1e-4)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_calculators_match_float64_oracle_on_synthetic(dev, tmp_path, engine):
+    """Well-separated slow modes: eigenvalues / eigenvectors within 1e-5 of float64."""
+    from deep_cartograph_b200.modules.cv_learning.cv_calculator import cv_calculators_map
+    n, f, lag, d = 30000, 256, 10, 4
+    X = synth_features(n, f, seed=9)
+    cfg = dict(_config(engine)["common"], dimension=d, lag_time=lag, num_subspaces=8, subspaces_dimension=5)
+    Z = oracle.standardize(X, *oracle.prepare_normalization(oracle.column_stats(X), "mean_std"))
+    for cv in ("pca", "tica", "htica"):
+        calc = cv_calculators_map[cv](configuration=cfg, output_path=str(tmp_path / cv))
+        calc.load_training_tensor(torch.from_numpy(X))
+        proj = calc.run(d)
+        assert proj is not None
+        if cv == "pca":
+            evals, W = oracle.pca(Z, d)
+        elif cv == "tica":
+            evals, W = oracle.tica(Z, lag, d)
+        else:
+            W, _, _ = oracle.htica(Z, lag, 8, 5, d)
+            evals = None
+        gap = 1.0
+        if evals is not None:
+            np.testing.assert_allclose(calc.eigenvalues, evals, rtol=1e-5)
+        np.testing.assert_allclose(calc.cv, W, atol=1e-5 * gap + 2e-7 * 50)
+        # projection of the training data, normalised to [-1, 1]
+        P = oracle.project(Z, W)
+        cm, cr = oracle.cv_normalization(P)
+        np.testing.assert_allclose(proj.to_numpy(), (P - cm) / cr, atol=1e-4)
+
+
+def test_traj_cluster_step_api_kmeans(dev, c1, tmp_path):
+    from deep_cartograph_b200.tools import traj_cluster
+    csv = tmp_path / "tica.csv"
+    pd.DataFrame(c1["tica_csv"], columns=list(c1["tica_csv_cols"])).to_csv(csv, index=False, float_format="%.4f")
+    cfg = {"algorithm": "kmeans", "search_interval": [3, 5], "n_init": 2}
+    out = traj_cluster(cfg, [str(csv)], output_folder=str(tmp_path / "cl"))
+    df = pd.read_csv(out["traj_0"][0])
+    assert list(df.columns) == ["TIC 1", "TIC 2", "traj_label", "cluster", "centroid", "frame"]
+    assert df["centroid"].sum() == df["cluster"].nunique()
+    # fixed-init path == oracle
+    init = c1["tica_csv"][:4].copy()
+    out = traj_cluster(cfg, [str(csv)], output_folder=str(tmp_path / "cl2"), initial_centroids=init)
+    df = pd.read_csv(out["traj_0"][0])
+    res = oracle.kmeans_lloyd(c1["tica_csv"], init)
+    diff = np.flatnonzero(df["cluster"].to_numpy() != res["labels"])
+    assert np.all(res["second"][diff] - res["best"][diff] <= 1e-9)
+
+
+def test_ops_reject_cpu_tensors():
+    from deep_cartograph_b200 import ops
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.column_stats(torch.zeros(4, 4))

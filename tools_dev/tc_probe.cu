@@ -1,0 +1,225 @@
+// Standalone tcgen05 probe (diagnostics only, not part of the product library).
+// Answers, on a real B200, the hardware questions the covariance engine's design rests on:
+//   1. kind::tf32 with MN-major, SWIZZLE_NONE shared-memory operands: layout + descriptor semantics,
+//      including a descriptor start address shifted by an arbitrary number of K rows (lag shift);
+//   2. A operand from TMEM (TS form) written with tcgen05.st.32x32b;
+//   3. issue rate of M=128 x N={128,256} x K=8 MMAs in SS and TS form;
+//   4. rounding behaviour of the FP32 accumulation over long K (truncation vs round-to-nearest);
+//   5. what the tensor core does with the low 13 mantissa bits of an fp32 operand.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tc_probe tc_probe.cu -lcuda
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "../deep_cartograph_b200/csrc/tc_common.cuh"
+
+using namespace dcg::tc;
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(2); } } while (0)
+
+constexpr int KROWS = 64;       // K rows staged in smem (8 K-steps)
+constexpr int PADROWS = 40;     // extra rows so a shifted window stays inside the buffer
+
+struct Params {
+  const float* A;   // [KROWS][128]
+  const float* B;   // [KROWS + PADROWS][N]
+  float* D;         // [128][N]
+  long long* cycles;
+  int N;
+  int mode;         // 0 = SS, 1 = TS
+  int shift;        // B window starts at row `shift`
+  int reps;         // the 8 K-steps are issued `reps` times (accumulating)
+  int a_mn;         // SS only: 1 = A stored MN-major (as B), 0 unused
+};
+
+__global__ void __launch_bounds__(128, 1) probe_kernel(Params p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int N = p.N;
+  const int RB = KROWS + PADROWS;                 // rows per MN-group in the B buffer
+  float* As = reinterpret_cast<float*>(smem);                       // [32 groups][KROWS][4]
+  float* Bs = reinterpret_cast<float*>(smem + 32 * KROWS * 16);     // [N/4 groups][RB][4]
+
+  // stage operands in the MN-major SWIZZLE_NONE canonical layout
+  for (int i = tid; i < KROWS * 128; i += 128) {
+    const int k = i / 128, m = i % 128;
+    As[((m >> 2) * KROWS + k) * 4 + (m & 3)] = p.A[i];
+  }
+  for (int i = tid; i < RB * N; i += 128) {
+    const int k = i / N, n = i % N;
+    Bs[((n >> 2) * RB + k) * 4 + (n & 3)] = p.B[i];
+  }
+  if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t a_tmem = tmem + 256;             // TS: A lives at columns [256, 256 + KROWS)
+
+  if (p.mode == 1) {
+    // thread m (lane 32*warp + lane of TMEM) holds A[k][m] for all k
+    for (int ks = 0; ks < KROWS / 8; ++ks) {
+      uint32_t v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = __float_as_uint(p.A[(ks * 8 + j) * 128 + tid]);
+      tmem_st_x8(a_tmem + ((uint32_t)(warp * 32) << 16) + ks * 8, v);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+  }
+  __syncthreads();
+  tc_fence_after();
+
+  long long t0 = 0, t1 = 0;
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc_tf32(128, N, p.mode == 0 ? 1 : 0, 1);
+    const uint32_t a_base = smem_u32(As), b_base = smem_u32(Bs) + p.shift * 16;
+    t0 = clock64();
+    for (int r = 0; r < p.reps; ++r) {
+#pragma unroll 1
+      for (int ks = 0; ks < KROWS / 8; ++ks) {
+        const uint64_t bdesc = make_smem_desc(b_base + ks * 128, 128, RB * 16);
+        const uint32_t acc = (r | ks) ? 1u : 0u;
+        if (p.mode == 0) {
+          const uint64_t adesc = make_smem_desc(a_base + ks * 128, 128, KROWS * 16);
+          mma_tf32_ss(tmem, adesc, bdesc, idesc, acc);
+        } else {
+          mma_tf32_ts(tmem, a_tmem + ks * 8, bdesc, idesc, acc);
+        }
+      }
+    }
+    mma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  if (tid == 0) { t1 = clock64(); p.cycles[0] = t1 - t0; }
+  tc_fence_after();
+  // epilogue: lane (= row m) x 32 columns at a time
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld_x32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) p.D[(size_t)tid * N + c0 + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+static float tf32_rn(float x) {   // round-to-nearest-even-ish (rna = ties away) to 10-bit mantissa
+  uint32_t u; memcpy(&u, &x, 4);
+  u += 0x1000u; u &= 0xFFFFE000u;
+  float r; memcpy(&r, &u, 4); return r;
+}
+static float tf32_trunc(float x) {
+  uint32_t u; memcpy(&u, &x, 4);
+  u &= 0xFFFFE000u;
+  float r; memcpy(&r, &u, 4); return r;
+}
+
+struct Result { double max_abs_err, mean_rel_err, max_rel_err; long long cycles; };
+
+static Result run(int N, int mode, int shift, int reps, const std::vector<float>& A, const std::vector<float>& B,
+                  int ref_round /*0 exact inputs, 1 rn, 2 trunc*/) {
+  const int RB = KROWS + PADROWS;
+  float *dA, *dB, *dD; long long* dC;
+  CK(cudaMalloc(&dA, A.size() * 4)); CK(cudaMalloc(&dB, B.size() * 4));
+  CK(cudaMalloc(&dD, 128 * N * 4)); CK(cudaMalloc(&dC, 8));
+  CK(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dD, 0, 128 * N * 4));
+  Params p{dA, dB, dD, dC, N, mode, shift, reps, 1};
+  const size_t smem = 32 * KROWS * 16 + (size_t)(N / 4) * RB * 16;
+  CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  probe_kernel<<<1, 128, smem>>>(p);
+  CK(cudaDeviceSynchronize());
+  std::vector<float> D(128 * N);
+  long long cyc;
+  CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&cyc, dC, 8, cudaMemcpyDeviceToHost));
+  Result res{0, 0, 0, cyc};
+  for (int m = 0; m < 128; ++m)
+    for (int n = 0; n < N; ++n) {
+      double s = 0;
+      for (int k = 0; k < KROWS; ++k) {
+        float a = A[k * 128 + m], b = B[(k + shift) * N + n];
+        if (ref_round == 1) { a = tf32_rn(a); b = tf32_rn(b); }
+        if (ref_round == 2) { a = tf32_trunc(a); b = tf32_trunc(b); }
+        s += (double)a * (double)b;
+      }
+      s *= reps;
+      const double e = (double)D[m * N + n] - s;
+      res.max_abs_err = fmax(res.max_abs_err, fabs(e));
+      if (s != 0) { res.mean_rel_err += e / s; res.max_rel_err = fmax(res.max_rel_err, fabs(e / s)); }
+    }
+  res.mean_rel_err /= 128.0 * N;
+  cudaFree(dA); cudaFree(dB); cudaFree(dD); cudaFree(dC);
+  return res;
+}
+
+int main() {
+  cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
+  printf("device %s cc %d.%d sms %d clock %d kHz\n", prop.name, prop.major, prop.minor, prop.multiProcessorCount, prop.clockRate);
+  const int RB = KROWS + PADROWS;
+  srand(1);
+  // 1/2: exact integer data: layout + descriptor + shift + TS
+  for (int N : {128, 256}) {
+    std::vector<float> A(KROWS * 128), B((size_t)RB * N);
+    for (auto& v : A) v = (float)(rand() % 17 - 8);
+    for (auto& v : B) v = (float)(rand() % 17 - 8);
+    for (int mode : {0, 1})
+      for (int shift : {0, 1, 10, 33}) {
+        Result r = run(N, mode, shift, 1, A, B, 0);
+        printf("exact  N=%d mode=%s shift=%2d : max_abs_err=%g  cycles=%lld\n", N, mode ? "TS" : "SS", shift, r.max_abs_err, r.cycles);
+      }
+  }
+  // 3: issue rate (reps x 8 MMAs)
+  for (int N : {128, 256}) {
+    std::vector<float> A(KROWS * 128, 1.0f), B((size_t)RB * N, 1.0f);
+    for (int mode : {0, 1})
+      for (int reps : {16, 256}) {
+        Result r = run(N, mode, 0, reps, A, B, 0);
+        printf("rate   N=%d mode=%s mmas=%5d : cycles=%lld  cycles/mma=%.1f  max_abs_err=%g\n", N, mode ? "TS" : "SS",
+               reps * 8, r.cycles, (double)r.cycles / (reps * 8), r.max_abs_err);
+      }
+  }
+  // 4: accumulation rounding: positive tf32-exact operands, long K
+  {
+    const int N = 128;
+    std::vector<float> A(KROWS * 128), B((size_t)RB * N);
+    for (auto& v : A) v = tf32_trunc(0.5f + (float)rand() / RAND_MAX);
+    for (auto& v : B) v = tf32_trunc(0.5f + (float)rand() / RAND_MAX);
+    for (int reps : {1, 4, 16, 64, 256, 1024}) {
+      Result r = run(N, 0, 0, reps, A, B, 0);
+      printf("accum  K=%6d : mean_rel_err=%+.3e max_rel_err=%.3e\n", reps * KROWS, r.mean_rel_err, r.max_rel_err);
+    }
+    // zero-mean operands (what standardised features look like)
+    for (auto& v : A) v = tf32_trunc(2.0f * (float)rand() / RAND_MAX - 1.0f);
+    for (auto& v : B) v = tf32_trunc(2.0f * (float)rand() / RAND_MAX - 1.0f);
+    for (int reps : {1, 16, 256}) {
+      Result r = run(N, 0, 0, reps, A, B, 0);
+      printf("accum0 K=%6d : max_abs_err=%.3e (|D| ~ %g)\n", reps * KROWS, r.max_abs_err, sqrt((double)reps * KROWS) / 3);
+    }
+  }
+  // 5: low mantissa bits: full fp32 operands vs references with rn / truncated inputs
+  {
+    const int N = 128;
+    std::vector<float> A(KROWS * 128), B((size_t)RB * N);
+    for (auto& v : A) v = 0.5f + (float)rand() / RAND_MAX;
+    for (auto& v : B) v = 0.5f + (float)rand() / RAND_MAX;
+    Result r0 = run(N, 0, 0, 1, A, B, 0), r1 = run(N, 0, 0, 1, A, B, 1), r2 = run(N, 0, 0, 1, A, B, 2);
+    printf("lowbits: max_rel_err vs exact-input ref %.3e | vs rn-input ref %.3e | vs trunc-input ref %.3e\n",
+           r0.max_rel_err, r1.max_rel_err, r2.max_rel_err);
+    Result t2 = run(N, 1, 0, 1, A, B, 2);
+    printf("lowbits(TS): vs trunc-input ref %.3e\n", t2.max_rel_err);
+  }
+  printf("probe done\n");
+  return 0;
+}
