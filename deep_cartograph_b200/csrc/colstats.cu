@@ -3,8 +3,9 @@
 //
 // Layout: X[n][ld]; a warp reads 32*VEC consecutive floats of one row (fully coalesced), the
 // CTA's 8 warps take 8 different rows per step; a CTA owns a (row block) x (column strip) tile.
-// Per thread: FP32 Welford over <= kRowsPerCta/8 rows (well conditioned even when |mean| >> std),
-// merged across the CTA and across row blocks in FP64 with Chan's formula.
+// Per thread: shifted FP32 sums over 4 rows at a time (shift = first row of the tile, so the sums
+// are conditioned by the column's spread even when |mean| >> std), promoted to FP64, then merged
+// across the CTA and across row blocks in FP64 with Chan's formula.
 // HBM-bound: 4*f bytes per frame, read once.
 #include "dcg_common.cuh"
 
@@ -44,47 +45,63 @@ colstats_partial_kernel(const float* __restrict__ X, int64_t n, int f, int64_t l
   const int64_t row_end = min(n, row_begin + kStatRowsPerCta);
   const bool active = col0 < f;                                // f % VEC == 0 guaranteed by host
 
-  float mean[VEC], m2[VEC], mn[VEC], mx[VEC];
+  // Shifted sums: d = x - K with K = the tile's first row of this column, so every FP32 quantity
+  // is of the size of the column's spread (not its mean).  FP32 partials are promoted to FP64
+  // every kStatUnroll rows; the per-thread result is (mean, M2) in FP64.
+  float shift[VEC], mn[VEC], mx[VEC];
+  double s64[VEC], q64[VEC];
 #pragma unroll
-  for (int v = 0; v < VEC; ++v) { mean[v] = 0.f; m2[v] = 0.f; mn[v] = INFINITY; mx[v] = -INFINITY; }
-  float cnt = 0.f;
+  for (int v = 0; v < VEC; ++v) { shift[v] = 0.f; s64[v] = 0.0; q64[v] = 0.0; mn[v] = INFINITY; mx[v] = -INFINITY; }
+  int cnt = 0;
 
   if (active) {
     const float* base = X + col0;
+    load_vec<VEC>(base + row_begin * ld, shift);
     int64_t r = row_begin + warp;
     // unrolled: kStatUnroll independent loads in flight per thread
     for (; r + (int64_t)(kStatUnroll - 1) * kStatWarps < row_end; r += (int64_t)kStatUnroll * kStatWarps) {
       float x[kStatUnroll][VEC];
 #pragma unroll
       for (int u = 0; u < kStatUnroll; ++u) load_vec<VEC>(base + (r + (int64_t)u * kStatWarps) * ld, x[u]);
+      float s[VEC], q[VEC];
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) { s[v] = 0.f; q[v] = 0.f; }
 #pragma unroll
       for (int u = 0; u < kStatUnroll; ++u) {
-        cnt += 1.f;
-        const float inv = __frcp_rn(cnt);
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
-          const float d = x[u][v] - mean[v];
-          mean[v] = fmaf(d, inv, mean[v]);
-          m2[v] = fmaf(d, x[u][v] - mean[v], m2[v]);
+          const float d = x[u][v] - shift[v];
+          s[v] += d;
+          q[v] = fmaf(d, d, q[v]);
           mn[v] = fminf(mn[v], x[u][v]);
           mx[v] = fmaxf(mx[v], x[u][v]);
         }
       }
+      cnt += kStatUnroll;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) { s64[v] += (double)s[v]; q64[v] += (double)q[v]; }
     }
     for (; r < row_end; r += kStatWarps) {
       float x[VEC];
       load_vec<VEC>(base + r * ld, x);
-      cnt += 1.f;
-      const float inv = __frcp_rn(cnt);
+      cnt += 1;
 #pragma unroll
       for (int v = 0; v < VEC; ++v) {
-        const float d = x[v] - mean[v];
-        mean[v] = fmaf(d, inv, mean[v]);
-        m2[v] = fmaf(d, x[v] - mean[v], m2[v]);
+        const float d = x[v] - shift[v];
+        s64[v] += (double)d;
+        q64[v] += (double)d * (double)d;
         mn[v] = fminf(mn[v], x[v]);
         mx[v] = fmaxf(mx[v], x[v]);
       }
     }
+  }
+  double mean[VEC], m2[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    const double c = cnt > 0 ? (double)cnt : 1.0;
+    const double ms = s64[v] / c;
+    mean[v] = (double)shift[v] + ms;
+    m2[v] = fmax(q64[v] - s64[v] * ms, 0.0);
   }
 
   // CTA merge (FP64 Chan) of the 8 warps' partials, per column.
@@ -95,8 +112,8 @@ colstats_partial_kernel(const float* __restrict__ X, int64_t n, int f, int64_t l
   __shared__ float s_mx[kStatWarps][32 * VEC];
 #pragma unroll
   for (int v = 0; v < VEC; ++v) {
-    s_mean[warp][lane * VEC + v] = (double)mean[v];
-    s_m2[warp][lane * VEC + v] = (double)m2[v];
+    s_mean[warp][lane * VEC + v] = mean[v];
+    s_m2[warp][lane * VEC + v] = m2[v];
     s_mn[warp][lane * VEC + v] = mn[v];
     s_mx[warp][lane * VEC + v] = mx[v];
   }

@@ -49,7 +49,7 @@ int dcg_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* ---- A2: per-feature statistics -------------------------------------------------------------
  * Replaces `training_df.agg(['mean','std','min','max'])`
  * (modules/cv_learning/cv_calculator.py:295-297).  Single pass over X (n x f, row stride ld
- * floats): per-thread FP32 Welford, FP64 Chan merge.  Outputs: mean[f], m2[f] (sum of squared
+ * floats): per-thread shifted FP32 sums promoted to FP64, FP64 Welford/Chan merge.  Outputs: mean[f], m2[f] (sum of squared
  * deviations from the mean; std(ddof=1) = sqrt(m2/(n-1))), minv[f], maxv[f].                  */
 size_t dcg_colstats_workspace_bytes(int64_t n, int f);
 int dcg_colstats_f32(const float* X, int64_t n, int f, int64_t ld,

@@ -14,6 +14,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
+#include <algorithm>
 #include "../deep_cartograph_b200/csrc/tc_common.cuh"
 
 using namespace dcg::tc;
@@ -32,7 +33,9 @@ struct Params {
   int mode;         // 0 = SS, 1 = TS
   int shift;        // B window starts at row `shift`
   int reps;         // the 8 K-steps are issued `reps` times (accumulating)
-  int a_mn;         // SS only: 1 = A stored MN-major (as B), 0 unused
+  int a_mn;         // SS only: 1 = A stored MN-major, 0 = K-major
+  int b_mn;         // 1 = B stored MN-major, 0 = K-major
+  int roundtrip;    // 1 = no MMA: tcgen05.st a pattern into D, read it back
 };
 
 __global__ void __launch_bounds__(128, 1) probe_kernel(Params p) {
@@ -46,13 +49,17 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(Params p) {
   float* Bs = reinterpret_cast<float*>(smem + 32 * KROWS * 16);     // [N/4 groups][RB][4]
 
   // stage operands in the MN-major SWIZZLE_NONE canonical layout
+  // MN-major: [mn/4][k][mn%4]          (core matrix = 4 mn x 8 k, 128 B; SBO = mn-group stride)
+  // K-major : [k/4][mn][k%4]           (core matrix = 8 mn x 4 k, 128 B; LBO = k-group stride, SBO = 8-row stride = 128)
   for (int i = tid; i < KROWS * 128; i += 128) {
     const int k = i / 128, m = i % 128;
-    As[((m >> 2) * KROWS + k) * 4 + (m & 3)] = p.A[i];
+    if (p.a_mn) As[((m >> 2) * KROWS + k) * 4 + (m & 3)] = p.A[i];
+    else As[((k >> 2) * 128 + m) * 4 + (k & 3)] = p.A[i];
   }
   for (int i = tid; i < RB * N; i += 128) {
     const int k = i / N, n = i % N;
-    Bs[((n >> 2) * RB + k) * 4 + (n & 3)] = p.B[i];
+    if (p.b_mn) Bs[((n >> 2) * RB + k) * 4 + (n & 3)] = p.B[i];
+    else Bs[((k >> 2) * N + n) * 4 + (k & 3)] = p.B[i];
   }
   if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
   if (warp == 0) tmem_alloc(&tmem_base_s, 512);
@@ -77,27 +84,48 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(Params p) {
   __syncthreads();
   tc_fence_after();
 
+  if (p.roundtrip) {
+    for (int c0 = 0; c0 < N; c0 += 8) {
+      uint32_t v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = __float_as_uint((float)(tid * 1000 + c0 + j));
+      tmem_st_x8(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
   long long t0 = 0, t1 = 0;
-  if (tid == 0) {
-    const uint32_t idesc = make_idesc_tf32(128, N, p.mode == 0 ? 1 : 0, 1);
+  if (tid == 0 && !p.roundtrip) {
+    const uint32_t idesc = make_idesc_tf32(128, N, p.mode == 0 ? p.a_mn : 0, p.b_mn);
     const uint32_t a_base = smem_u32(As), b_base = smem_u32(Bs) + p.shift * 16;
+    // descriptors precomputed: the timed loop only issues
+    uint64_t bd[KROWS / 8], ad[KROWS / 8];
+#pragma unroll
+    for (int ks = 0; ks < KROWS / 8; ++ks) {
+      // MN-major: K step = 8 rows x 16 B = 128 B, SBO = group stride
+      // K-major : K step = 2 k-groups; LBO = k-group stride, SBO = 128 (8 rows x 16 B); shift must be a multiple of 4
+      bd[ks] = p.b_mn ? make_smem_desc(b_base + ks * 128, 128, RB * 16)
+                      : make_smem_desc(smem_u32(Bs) + (ks * 2 + p.shift / 4) * N * 16, N * 16, 128);
+      ad[ks] = p.a_mn ? make_smem_desc(a_base + ks * 128, 128, KROWS * 16)
+                      : make_smem_desc(a_base + ks * 2 * 128 * 16, 128 * 16, 128);
+    }
     t0 = clock64();
-    for (int r = 0; r < p.reps; ++r) {
-#pragma unroll 1
-      for (int ks = 0; ks < KROWS / 8; ++ks) {
-        const uint64_t bdesc = make_smem_desc(b_base + ks * 128, 128, RB * 16);
-        const uint32_t acc = (r | ks) ? 1u : 0u;
-        if (p.mode == 0) {
-          const uint64_t adesc = make_smem_desc(a_base + ks * 128, 128, KROWS * 16);
-          mma_tf32_ss(tmem, adesc, bdesc, idesc, acc);
-        } else {
-          mma_tf32_ts(tmem, a_tmem + ks * 8, bdesc, idesc, acc);
-        }
+    if (p.mode == 0) {
+      for (int r = 0; r < p.reps; ++r) {
+#pragma unroll
+        for (int ks = 0; ks < KROWS / 8; ++ks) mma_tf32_ss(tmem, ad[ks], bd[ks], idesc, (r | ks) ? 1u : 0u);
+      }
+    } else {
+      for (int r = 0; r < p.reps; ++r) {
+#pragma unroll
+        for (int ks = 0; ks < KROWS / 8; ++ks) mma_tf32_ts(tmem, a_tmem + ks * 8, bd[ks], idesc, (r | ks) ? 1u : 0u);
       }
     }
     mma_commit(&bar);
   }
-  mbar_wait(&bar, 0);
+  if (!p.roundtrip) mbar_wait(&bar, 0);
   if (tid == 0) { t1 = clock64(); p.cycles[0] = t1 - t0; }
   tc_fence_after();
   // epilogue: lane (= row m) x 32 columns at a time
@@ -126,6 +154,7 @@ static float tf32_trunc(float x) {
 
 struct Result { double max_abs_err, mean_rel_err, max_rel_err; long long cycles; };
 
+static int g_a_mn = 1, g_b_mn = 1, g_roundtrip = 0, g_verbose = 0;
 static Result run(int N, int mode, int shift, int reps, const std::vector<float>& A, const std::vector<float>& B,
                   int ref_round /*0 exact inputs, 1 rn, 2 trunc*/) {
   const int RB = KROWS + PADROWS;
@@ -135,7 +164,7 @@ static Result run(int N, int mode, int shift, int reps, const std::vector<float>
   CK(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice));
   CK(cudaMemset(dD, 0, 128 * N * 4));
-  Params p{dA, dB, dD, dC, N, mode, shift, reps, 1};
+  Params p{dA, dB, dD, dC, N, mode, shift, reps, g_a_mn, g_b_mn, g_roundtrip};
   const size_t smem = 32 * KROWS * 16 + (size_t)(N / 4) * RB * 16;
   CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   probe_kernel<<<1, 128, smem>>>(p);
@@ -145,6 +174,23 @@ static Result run(int N, int mode, int shift, int reps, const std::vector<float>
   CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(&cyc, dC, 8, cudaMemcpyDeviceToHost));
   Result res{0, 0, 0, cyc};
+  if (g_roundtrip) {
+    double bad = 0;
+    for (int m = 0; m < 128; ++m) for (int n = 0; n < N; ++n) bad += D[m * N + n] != (float)(m * 1000 + n);
+    res.max_abs_err = bad;
+    return res;
+  }
+  if (g_verbose) {
+    int exact = 0, nz = 0;
+    std::vector<double> ref(128 * N);
+    for (int m = 0; m < 128; ++m) for (int n = 0; n < N; ++n) {
+      double s2 = 0; for (int k = 0; k < KROWS; ++k) s2 += (double)A[k * 128 + m] * (double)B[(k + shift) * N + n];
+      ref[m * N + n] = s2 * reps; exact += D[m * N + n] == (float)(s2 * reps); nz += D[m * N + n] != 0.f;
+    }
+    printf("   exact=%d/%d nonzero=%d  D[0][0..5]= %g %g %g %g %g %g | ref %g %g %g %g %g %g | D[1][0]=%g ref %g D[5][7]=%g ref %g\n",
+           exact, 128 * N, nz, D[0], D[1], D[2], D[3], D[4], D[5], ref[0], ref[1], ref[2], ref[3], ref[4], ref[5],
+           D[N], ref[N], D[5 * N + 7], ref[5 * N + 7]);
+  }
   for (int m = 0; m < 128; ++m)
     for (int n = 0; n < N; ++n) {
       double s = 0;
@@ -169,13 +215,47 @@ int main() {
   printf("device %s cc %d.%d sms %d clock %d kHz\n", prop.name, prop.major, prop.minor, prop.multiProcessorCount, prop.clockRate);
   const int RB = KROWS + PADROWS;
   srand(1);
+  // 0: TMEM st -> ld round trip (no MMA)
+  {
+    std::vector<float> A(KROWS * 128, 0.f), B((size_t)RB * 128, 0.f);
+    g_roundtrip = 1;
+    Result r = run(128, 0, 0, 1, A, B, 0);
+    printf("tmem st/ld roundtrip: mismatches=%g\n", r.max_abs_err);
+    g_roundtrip = 0;
+  }
+  // 0b: layout controls on integer data, verbose
+  g_verbose = 1;
+  {
+    const int N = 128;
+    std::vector<float> A(KROWS * 128), B((size_t)RB * N);
+    for (auto& v : A) v = (float)(rand() % 17 - 8);
+    for (auto& v : B) v = (float)(rand() % 17 - 8);
+    for (int amn : {0, 1}) for (int bmn : {0, 1}) {
+      g_a_mn = amn; g_b_mn = bmn;
+      Result r = run(N, 0, 0, 1, A, B, 0);
+      printf("layout SS a_mn=%d b_mn=%d : max_abs_err=%g\n", amn, bmn, r.max_abs_err);
+    }
+    for (int bmn : {0, 1}) {
+      g_a_mn = 1; g_b_mn = bmn;
+      Result r = run(N, 1, 0, 1, A, B, 0);
+      printf("layout TS b_mn=%d : max_abs_err=%g\n", bmn, r.max_abs_err);
+    }
+    g_a_mn = 1; g_b_mn = 1;
+    // single hot element: A[k=0][m=0] = 1, B[k=0][n] = n + 1
+    std::fill(A.begin(), A.end(), 0.f); std::fill(B.begin(), B.end(), 0.f);
+    A[0] = 1.f; for (int n = 0; n < N; ++n) B[n] = (float)(n + 1);
+    for (int bmn : {0, 1}) { g_b_mn = bmn; Result r = run(N, 0, 0, 1, A, B, 0); printf("hot SS b_mn=%d a_mn=1: err=%g\n", bmn, r.max_abs_err); }
+    g_b_mn = 1;
+  }
+  g_verbose = 0;
+  g_a_mn = 0; g_b_mn = 0;
   // 1/2: exact integer data: layout + descriptor + shift + TS
   for (int N : {128, 256}) {
     std::vector<float> A(KROWS * 128), B((size_t)RB * N);
     for (auto& v : A) v = (float)(rand() % 17 - 8);
     for (auto& v : B) v = (float)(rand() % 17 - 8);
     for (int mode : {0, 1})
-      for (int shift : {0, 1, 10, 33}) {
+      for (int shift : {0, 4, 8, 36}) {
         Result r = run(N, mode, shift, 1, A, B, 0);
         printf("exact  N=%d mode=%s shift=%2d : max_abs_err=%g  cycles=%lld\n", N, mode ? "TS" : "SS", shift, r.max_abs_err, r.cycles);
       }
