@@ -2,28 +2,33 @@
 //
 // Computes, for 128 x 128 tiles (I, J) of the feature axis and a range of frames,
 //     S0[I,J]  += sum_t z_t[I] (x) z_t[J]         St[I,J] += sum_t z_t[I] (x) z_{t+lag}[J]
-// as a dense contraction over the FRAME axis on the 5th-generation tensor cores:
-//   * D (FP32 accumulators for S0 and St) in TMEM, columns [0,128) and [128,256);
-//   * A = z_t[I]^T (M = 128 features x K = 8 frames per MMA), standardised and split hi/lo by the
-//     A-producer warps straight from global memory into TMEM (tcgen05.st; TS form) -- or, in the
-//     SS variant, into shared memory;
-//   * B = z_t[J] (N = 128 features), standardised and split by the B-producer warps into a shared-
-//     memory RING of frames in the MN-major SWIZZLE_NONE canonical layout [feature/4][frame][4].
-//     Frames are the K axis and advance linearly (16 bytes per frame) inside a feature group, so
-//     the lag-shifted operand z_{t+lag}[J] is THE SAME ring read through a descriptor whose start
-//     address is advanced by lag*16 bytes: S0 and St share every staged byte.
-//   * split precision (3xTF32): D += Ahi*Bhi + Ahi*Blo + Alo*Bhi keeps ~2^-21 relative accuracy;
-//   * every `kc` frames the FP32 accumulators are flushed into a CTA-private FP64 slab
-//     (L2-resident), and at the end of a work item the slab is added to the FP64 result with
-//     red.global.add.f64.
-// Persistent CTAs (one per SM), dynamic work-item scheduler, warp-specialised roles connected by
-// mbarrier pipelines:   warps 0-3 A producers | 4-7 B producers | 8-11 epilogue | 12 MMA issuer.
+// as a dense contraction over the FRAME axis on the 5th-generation tensor cores
+// (tcgen05.mma kind::tf32, M = N = 128, K = 8 frames per instruction, cta_group::1).
+//
+// Operands.  X is row-major (frames x features), so the contraction axis (frames) is the slow
+// one in memory.  kind::tf32 takes K-major operands only (measured: tools_dev/tc_probe.cu; the
+// MN-major SWIZZLE_NONE form returns zeros), so the producer warps transpose while staging: a
+// thread owns ONE feature, reads 16 consecutive frames of it (each load instruction is a
+// coalesced 128-byte row segment across the warp), standardises, splits into TF32 hi + lo, and
+// writes 4-frame groups as 16-byte chunks into the K-major SWIZZLE_NONE canonical layout
+//     [frame group (4 frames)][feature row 0..127][4 frames]      (core matrix = 8 rows x 16 B)
+// Three operand tiles per 16-frame stage: A = z_t[I], B0 = z_t[J], Bt = z_{t+lag}[J], each as a
+// hi and a lo plane (6 x 8 KB per stage, 4 stages).  Diagonal tiles (I == J) reuse A as B0.
+//
+// Precision.  3xTF32: D += Ahi*Bhi + Ahi*Blo + Alo*Bhi (hi = RN_tf32(z), lo = RN_tf32(z - hi)).
+// The tensor core adds into its FP32 accumulator with truncation (measured: -5e-8 relative per
+// MMA on same-sign sums), so accumulation is two-level: level-1 accumulators (TMEM columns
+// [0,256)) take `kc` frames (default 128), then the epilogue warps add them with round-to-
+// nearest into level-2 FP32 accumulators (TMEM columns [256,512)); at the end of a work item
+// (<= 16384 frames) level 2 is added to the FP64 result with red.global.add.f64.
+//
+// Persistent CTAs (one per SM, static strided work-item schedule), warp-specialised roles joined
+// by mbarrier pipelines:  warps 0-3 A | 4-7 B0 | 8-11 Bt producers | 12 MMA issuer | 13-16 epilogue.
 //
 // Roofline: tensor pipe.  Algorithmic work 3*F^2 FLOP per frame pair (2F^2 for St + F^2 for the
-// upper triangle of S0); issued MMA FLOPs = 3x that for 3xTF32.  X is re-read once per tile row/
-// column from L2 (work items of the same frame range run concurrently).
+// upper triangle of S0); issued MMA FLOPs = 3x that for 3xTF32.  X is re-read once per tile row
+// and column from L2 (work items of the same frame range run concurrently).
 #include <cstdlib>
-#include <vector>
 #include "dcg_common.cuh"
 #include "cov_engines.cuh"
 #include "tc_common.cuh"
@@ -32,270 +37,190 @@ namespace dcg {
 
 using namespace tc;
 
-constexpr int kTile = 128;          // UMMA M = N = 128 features
-constexpr int kStage = 16;          // frames per pipeline stage (two K = 8 MMA steps)
-constexpr int kThreads = 13 * 32;   // 4 A-producer + 4 B-producer + 4 epilogue + 1 MMA warp
-constexpr int kSlabElems = kTile * kTile;
-
-template <bool A_TMEM> struct TcCfg;
-template <> struct TcCfg<true> {    // A operand in TMEM: shared memory holds only the B ring
-  static constexpr int NA = 8;      // 8 stages x 32 TMEM columns (16 hi + 16 lo) = columns [256,512)
-  static constexpr int NB = 10;     // 160-frame ring
-};
-template <> struct TcCfg<false> {   // A operand in shared memory as well
-  static constexpr int NA = 4;
-  static constexpr int NB = 6;      // 96-frame ring
-};
-template <bool A_TMEM> __host__ __device__ constexpr int tc_rb() { return TcCfg<A_TMEM>::NB * kStage; }
-template <bool A_TMEM> __host__ __device__ constexpr int tc_rb_alloc() { return tc_rb<A_TMEM>() + 7; }   // odd, + wrap copies
-template <bool A_TMEM> __host__ __device__ constexpr int tc_ra_alloc() { return A_TMEM ? 0 : TcCfg<A_TMEM>::NA * kStage + 1; }  // odd
-// the ring must hold the frames [t, t + lag + 8) of the current stage plus two stages of run-ahead
-template <bool A_TMEM> __host__ __device__ constexpr int tc_max_lag() { return tc_rb<A_TMEM>() - 3 * kStage; }
-template <bool A_TMEM> __host__ __device__ constexpr size_t tc_smem_bytes() {
-  return (size_t)2 * 32 * tc_rb_alloc<A_TMEM>() * 16 + (size_t)2 * 32 * tc_ra_alloc<A_TMEM>() * 16 + 1024;
-}
+constexpr int kTile = 128;           // UMMA M = N = 128 features
+constexpr int kStage = 16;           // frames per pipeline stage (two K = 8 MMA steps)
+constexpr int kNS = 4;               // pipeline stages
+constexpr int kProdWarps = 12;       // 4 per operand tile (A, B0, Bt)
+constexpr int kEpiWarps = 4;
+constexpr int kMmaWarp = kProdWarps;
+constexpr int kThreads = (kProdWarps + 1 + kEpiWarps) * 32;   // 544
+constexpr int kGroupBytes = kTile * 16;                       // one 4-frame group of 128 rows
+constexpr int kPlaneBytes = (kStage / 4) * kGroupBytes;       // 8 KB: one operand plane (hi or lo)
+constexpr int kStageBytes = 6 * kPlaneBytes;                  // A_hi A_lo B0_hi B0_lo Bt_hi Bt_lo
+constexpr size_t kSmemBytes = (size_t)kNS * kStageBytes + 1024;
+constexpr int kMaxItemFrames = 16384;                         // level-2 FP32 accumulation span
 
 __host__ __device__ inline bool tc_tile_needed(int i0, int j0, int f, int block, bool s0) {
-  if (s0 && j0 + kTile - 1 < i0) return false;
+  if (s0 && j0 + kTile - 1 < i0) return false;          // strictly-lower tile of the symmetric S0
   if (block <= 0) return true;
   const int ie = (i0 + kTile < f ? i0 + kTile : f) - 1, je = (j0 + kTile < f ? j0 + kTile : f) - 1;
   const int ia = i0 / block, ib = ie / block, ja = j0 / block, jb = je / block;
   return !(ib < ja || jb < ia);
 }
 
-struct TcPlan {
-  int nt;            // tiles per axis
-  int n_full;        // tiles needing S0 and St (cost 2)
-  int n_half;        // tiles needing only one of them (cost 1)
-  int per_round;     // items per round of two granules
-  int64_t granule;   // frames per granule (multiple of kStage)
-  int64_t rounds;
-  int64_t n_items;
-};
-
-static TcPlan tc_make_plan(int64_t M, int f, int block, bool want_s0, bool want_st, int* full, int* half) {
-  TcPlan p{};
-  p.nt = (int)ceil_div(f, kTile);
-  for (int ti = 0; ti < p.nt; ++ti)
-    for (int tj = 0; tj < p.nt; ++tj) {
-      const bool a = want_s0 && tc_tile_needed(ti * kTile, tj * kTile, f, block, true);
-      const bool b = want_st && tc_tile_needed(ti * kTile, tj * kTile, f, block, false);
-      if (a && b) { if (full) full[p.n_full] = ti * p.nt + tj; ++p.n_full; }
-      else if (a || b) { if (half) half[p.n_half] = (ti * p.nt + tj) | (a ? 0 : (1 << 30)); ++p.n_half; }
-    }
-  p.per_round = 2 * p.n_full + p.n_half;
-  if (p.per_round == 0) { p.n_items = 0; return p; }
-  const int64_t target_items = (int64_t)kNumSMs * 16;
-  int64_t rounds = std::max<int64_t>(1, target_items / p.per_round);
-  int64_t g = ceil_div(ceil_div(M, 2 * rounds), kStage) * kStage;
-  g = std::max<int64_t>(g, 4 * kStage);
-  p.granule = g;
-  p.rounds = ceil_div(M, 2 * g);
-  p.n_items = p.rounds * p.per_round;
-  return p;
-}
+constexpr int kFlagS0 = 1 << 29, kFlagSt = 1 << 30;
 
 struct TcParams {
   const float* X;
   int64_t n_rows, ld;
-  int f, lag, block;
+  int f, lag;
   const float* mean;
   const float* range;
   double* S0;
   double* St;
-  const int* full_tiles;
-  const int* half_tiles;
-  int* counter;
-  double* slabs;       // [grid][2][128*128], column-major per tile: slab[col*128 + row]
-  TcPlan plan;
-  int kc;              // frames between FP32 -> FP64 flushes (multiple of kStage)
+  const int* tiles;     // [n_tiles]: (ti * nt + tj) | flags
+  int n_tiles, nt;
+  int64_t granule;      // frames per work item (multiple of kc)
+  int64_t n_items;      // n_tiles * n_ranges, range-major
+  int kc;               // frames per level-1 chunk (multiple of kStage)
 };
 
-__global__ void tc_reset_kernel(int* counter) { *counter = 0; }
+// Tile list: (ti * nt + tj) | flags, tiles needing both matrices first.  One thread; nt <= ~40.
+__global__ void tc_plan_kernel(int* __restrict__ tiles, int nt, int f, int block, bool want_s0, bool want_st) {
+  if (threadIdx.x != 0) return;
+  int n = 0;
+  for (int pass = 0; pass < 2; ++pass)
+    for (int ti = 0; ti < nt; ++ti)
+      for (int tj = 0; tj < nt; ++tj) {
+        const bool s0 = want_s0 && tc_tile_needed(ti * kTile, tj * kTile, f, block, true);
+        const bool stt = want_st && tc_tile_needed(ti * kTile, tj * kTile, f, block, false);
+        if (!s0 && !stt) continue;
+        if ((pass == 0) != (s0 && stt)) continue;
+        tiles[n++] = (ti * nt + tj) | (s0 ? kFlagS0 : 0) | (stt ? kFlagSt : 0);
+      }
+}
 
-template <bool A_TMEM, bool X3, bool STD, bool VEC4>
+template <bool X3, bool STD>
 __global__ void __launch_bounds__(kThreads, 1) cov_tc_kernel(const TcParams p) {
-  using Cfg = TcCfg<A_TMEM>;
-  constexpr int NA = Cfg::NA, NB = Cfg::NB;
-  constexpr int RB = tc_rb<A_TMEM>(), RBA = tc_rb_alloc<A_TMEM>(), RAA = tc_ra_alloc<A_TMEM>();
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-  unsigned char* b_hi = smem;                                   // [32 groups][RBA rows][16 B]
-  unsigned char* b_lo = b_hi + (size_t)32 * RBA * 16;
-  unsigned char* a_hi_s = b_lo + (size_t)32 * RBA * 16;         // SS variant only: [32][RAA][16 B]
-  unsigned char* a_lo_s = a_hi_s + (size_t)32 * RAA * 16;
-
-  __shared__ uint64_t a_full[NA], a_empty[NA], b_full[NB], b_empty[NB], acc_full, acc_empty;
+  __shared__ uint64_t full_bar[kNS], empty_bar[kNS], acc_full, acc_empty;
   __shared__ uint32_t tmem_base_s;
-  __shared__ int s_item;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 4); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < NB; ++i) { mbar_init(&b_full[i], 4); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < kNS; ++i) { mbar_init(&full_bar[i], kProdWarps); mbar_init(&empty_bar[i], 1); }
     mbar_init(&acc_full, 1);
-    mbar_init(&acc_empty, 4);
+    mbar_init(&acc_empty, kEpiWarps);
     fence_barrier_init();
   }
-  if (warp == 12) tmem_alloc(&tmem_base_s, 512);
+  if (warp == kMmaWarp) tmem_alloc(&tmem_base_s, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
-  const uint32_t d0_t = tmem, dt_t = tmem + kTile, a_t = tmem + 2 * kTile;
+  const uint32_t l1_0 = tmem, l1_t = tmem + kTile, l2_0 = tmem + 2 * kTile, l2_t = tmem + 3 * kTile;
 
-  // running pipeline counters (identical in every role; they persist across work items)
-  uint32_t ga = 0, gb = 0, gc = 0;    // A stages, B stages, accumulator chunks consumed so far
   const int64_t M = p.n_rows - p.lag;
-  double* slab0 = p.slabs + (size_t)blockIdx.x * 2 * kSlabElems;
-  double* slabt = slab0 + kSlabElems;
+  const uint32_t chunk_stages = (uint32_t)(p.kc / kStage);
+  uint32_t gs = 0, gc = 0;      // pipeline stages / accumulator chunks consumed so far (all roles agree)
 
-  for (;;) {
-    __syncthreads();
-    if (tid == 0) s_item = atomicAdd(p.counter, 1);
-    __syncthreads();
-    const int64_t item = s_item;
-    if (item >= p.plan.n_items) break;
+  for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+    // ---- decode the work item: (frame range, tile, which matrices) ---------------------------
+    const int64_t range = item / p.n_tiles;
+    const int code = p.tiles[item - range * p.n_tiles];
+    const int tile = code & (kFlagS0 - 1);
+    const bool do_s0 = code & kFlagS0, do_st = code & kFlagSt;
+    const int64_t f0 = range * p.granule;
+    const int64_t f1 = f0 + p.granule < M ? f0 + p.granule : M;
+    const int i0 = (tile / p.nt) * kTile, j0 = (tile % p.nt) * kTile;
+    const bool diag = i0 == j0;
+    const uint32_t nS = (uint32_t)((f1 - f0 + kStage - 1) / kStage);
+    const uint32_t nC = (nS + chunk_stages - 1) / chunk_stages;
 
-    // ---- decode the work item: (tile, which matrices, frame range) --------------------------
-    const int64_t round = item / p.plan.per_round;
-    const int rem = (int)(item - round * p.plan.per_round);
-    int tile, do_s0, do_st;
-    int64_t f0, f1;
-    if (rem < 2 * p.plan.n_full) {
-      const int g = rem / p.plan.n_full;
-      tile = p.full_tiles[rem - g * p.plan.n_full];
-      do_s0 = p.S0 != nullptr; do_st = p.St != nullptr;
-      f0 = (2 * round + g) * p.plan.granule;
-      f1 = f0 + p.plan.granule;
-    } else {
-      const int code = p.half_tiles[rem - 2 * p.plan.n_full];
-      tile = code & ~(1 << 30);
-      do_s0 = !(code >> 30); do_st = code >> 30;
-      f0 = 2 * round * p.plan.granule;
-      f1 = f0 + 2 * p.plan.granule;
-    }
-    if (f1 > M) f1 = M;
-    if (f0 >= f1) continue;                         // uniform across the CTA
-    const int i0 = (tile / p.plan.nt) * kTile, j0 = (tile % p.plan.nt) * kTile;
-    const int lag = do_st ? p.lag : 0;              // S0-only items need no look-ahead
-    const int64_t frames = f1 - f0;
-    const uint32_t nA = (uint32_t)((frames + kStage - 1) / kStage);
-    const uint32_t nB = nA + (uint32_t)((lag + kStage - 1) / kStage);   // covers every frame any MMA reads
-    const uint32_t kc_stages = (uint32_t)(p.kc / kStage);
-    const uint32_t nC = (nA + kc_stages - 1) / kc_stages;
-
-    if (warp < 4) {
-      // =============================== A producers ===========================================
-      const int m = tid;                             // feature row of the tile == TMEM lane
-      const int col = i0 + m;
+    if (warp < kProdWarps) {
+      // =============================== producers ==============================================
+      const int op = warp >> 2;                       // 0 = A, 1 = B0, 2 = Bt
+      const int row = (warp & 3) * 32 + lane;         // feature row of the tile
+      const bool needed = op == 0 || (op == 1 ? (do_s0 && !diag) : do_st);
+      const int col = (op == 0 ? i0 : j0) + row;
       const bool col_ok = col < p.f;
+      const int shift = op == 2 ? p.lag : 0;
+      // A rows beyond the item's range must be exactly zero; B rows only need to be in bounds
+      const int64_t t_lim = op == 0 ? f1 : p.n_rows - shift;
       float mu = 0.f, rg = 1.f, ri = 1.f;
       if (STD && col_ok) { mu = p.mean[col]; rg = p.range[col]; ri = 1.0f / rg; }
-      const float* xcol = p.X + col;
-      for (uint32_t sa = 0; sa < nA; ++sa, ++ga) {
-        const uint32_t slot = ga % NA;
-        mbar_wait(&a_empty[slot], ((ga / NA) & 1) ^ 1);
-        const int64_t t0 = f0 + (int64_t)sa * kStage;
-        float x[kStage];
-#pragma unroll
-        for (int j = 0; j < kStage; ++j) {
-          const int64_t t = t0 + j;
-          x[j] = (col_ok && t < f1) ? __ldg(xcol + t * p.ld) : mu;     // mu -> z == 0 exactly
-        }
-        uint32_t hi[kStage], lo[kStage];
-#pragma unroll
-        for (int j = 0; j < kStage; ++j) {
-          const float z = STD ? standardize1(x[j], mu, rg, ri) : x[j];
-          split_tf32(z, hi[j], lo[j]);
-        }
-        if constexpr (A_TMEM) {
-          tc_fence_after();
-          const uint32_t base = a_t + ((uint32_t)(warp * 32) << 16) + slot * 32;
-          tmem_st_x16(base, hi);
-          if (X3) tmem_st_x16(base + 16, lo);
-          tmem_st_wait();
-          tc_fence_before();
-        } else {
-          // [group = m/4][row][m%4]
-          float* ah = reinterpret_cast<float*>(a_hi_s) + ((size_t)(m >> 2) * RAA + slot * kStage) * 4 + (m & 3);
-          float* al = reinterpret_cast<float*>(a_lo_s) + ((size_t)(m >> 2) * RAA + slot * kStage) * 4 + (m & 3);
+      const float* xcol = p.X + (int64_t)shift * p.ld + col;
+      unsigned char* plane_hi = smem + (size_t)(2 * op) * kPlaneBytes + (size_t)row * 16;
+      for (uint32_t s = 0; s < nS; ++s, ++gs) {
+        const uint32_t slot = gs % kNS;
+        if (needed) {
+          const int64_t t0 = f0 + (int64_t)s * kStage;
+          float x[kStage];
 #pragma unroll
           for (int j = 0; j < kStage; ++j) {
-            ah[j * 4] = __uint_as_float(hi[j]);
-            if (X3) al[j * 4] = __uint_as_float(lo[j]);
+            const int64_t t = t0 + j;
+            x[j] = (col_ok && t < t_lim) ? __ldg(xcol + t * p.ld) : mu;     // mu -> z == 0 exactly
+          }
+          mbar_wait(&empty_bar[slot], ((gs / kNS) & 1) ^ 1);
+          unsigned char* dst = plane_hi + (size_t)slot * kStageBytes;
+#pragma unroll
+          for (int g = 0; g < kStage / 4; ++g) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              const float z = STD ? standardize1(x[4 * g + v], mu, rg, ri) : x[4 * g + v];
+              split_tf32(z, hi[v], lo[v]);
+            }
+            *reinterpret_cast<uint4*>(dst + g * kGroupBytes) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            if (X3) *reinterpret_cast<uint4*>(dst + kPlaneBytes + g * kGroupBytes) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
           fence_proxy_async_smem();
+        } else {
+          mbar_wait(&empty_bar[slot], ((gs / kNS) & 1) ^ 1);
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&a_full[slot]);
+        if (lane == 0) mbar_arrive(&full_bar[slot]);
       }
-      gb += nB; gc += nC;
-    } else if (warp < 8) {
-      // =============================== B producers ===========================================
-      const int w = warp - 4;                        // rows w, w+4, w+8, w+12 of every stage
-      const int c = j0 + lane * 4;                   // 4 feature columns == one MN group
-      float mu[4], rg[4], ri[4];
-      bool ok[4];
+      gc += nC;
+    } else if (warp == kMmaWarp) {
+      // =============================== MMA issuer ============================================
+      if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc_tf32(kTile, kTile, 0, 0);   // both operands K-major
+        const uint32_t sbase = smem_u32(smem);
+        for (uint32_t s = 0; s < nS; ++s, ++gs) {
+          const uint32_t slot = gs % kNS;
+          const bool chunk_first = (s % chunk_stages) == 0;
+          if (chunk_first) mbar_wait(&acc_empty, (gc & 1) ^ 1);          // level-1 accumulators drained
+          mbar_wait(&full_bar[slot], (gs / kNS) & 1);
+          tc_fence_after();
+          const uint32_t st_base = sbase + slot * kStageBytes;
 #pragma unroll
-      for (int v = 0; v < 4; ++v) {
-        ok[v] = c + v < p.f;
-        mu[v] = 0.f; rg[v] = 1.f;
-        if (STD && ok[v]) { mu[v] = p.mean[c + v]; rg[v] = p.range[c + v]; }
-        ri[v] = 1.0f / rg[v];
-      }
-      const int64_t t_last = f1 + lag;               // frames [f0, t_last) are staged; t_last <= n_rows
-      for (uint32_t sb = 0; sb < nB; ++sb, ++gb) {
-        const uint32_t slot = gb % NB;
-        mbar_wait(&b_empty[slot], ((gb / NB) & 1) ^ 1);
-        const int64_t t0 = f0 + (int64_t)sb * kStage;
-        float x[4][4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const int64_t t = t0 + w + 4 * r;
-          const float* xp = p.X + t * p.ld + c;
-          if (t < t_last) {
-            if (VEC4 && ok[3]) {
-              const float4 q = ldg_stream4(xp);
-              x[r][0] = q.x; x[r][1] = q.y; x[r][2] = q.z; x[r][3] = q.w;
-            } else {
-#pragma unroll
-              for (int v = 0; v < 4; ++v) x[r][v] = ok[v] ? __ldg(xp + v) : mu[v];
+          for (int h = 0; h < kStage / 8; ++h) {
+            const uint32_t off = (uint32_t)h * 2 * kGroupBytes;             // K = 8 = two 4-frame groups
+            const uint32_t acc = (chunk_first && h == 0) ? 0u : 1u;
+            const uint64_t a_h = make_smem_desc(st_base + 0 * kPlaneBytes + off, kGroupBytes, 128);
+            const uint64_t a_l = make_smem_desc(st_base + 1 * kPlaneBytes + off, kGroupBytes, 128);
+            if (do_s0) {
+              const uint64_t b_h = diag ? a_h : make_smem_desc(st_base + 2 * kPlaneBytes + off, kGroupBytes, 128);
+              const uint64_t b_l = diag ? a_l : make_smem_desc(st_base + 3 * kPlaneBytes + off, kGroupBytes, 128);
+              mma_tf32_ss(l1_0, a_h, b_h, idesc, acc);
+              if (X3) { mma_tf32_ss(l1_0, a_h, b_l, idesc, 1); mma_tf32_ss(l1_0, a_l, b_h, idesc, 1); }
             }
-          } else {
-#pragma unroll
-            for (int v = 0; v < 4; ++v) x[r][v] = mu[v];
+            if (do_st) {
+              const uint64_t b_h = make_smem_desc(st_base + 4 * kPlaneBytes + off, kGroupBytes, 128);
+              const uint64_t b_l = make_smem_desc(st_base + 5 * kPlaneBytes + off, kGroupBytes, 128);
+              mma_tf32_ss(l1_t, a_h, b_h, idesc, acc);
+              if (X3) { mma_tf32_ss(l1_t, a_h, b_l, idesc, 1); mma_tf32_ss(l1_t, a_l, b_h, idesc, 1); }
+            }
+          }
+          mma_commit(&empty_bar[slot]);                                    // stage consumed
+          if ((s + 1) % chunk_stages == 0 || s + 1 == nS) {
+            mma_commit(&acc_full);                                         // chunk ready to drain
+            ++gc;
           }
         }
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          uint32_t hi[4], lo[4];
-#pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            const float z = (STD && ok[v]) ? standardize1(x[r][v], mu[v], rg[v], ri[v]) : (ok[v] ? x[r][v] : 0.f);
-            split_tf32(z, hi[v], lo[v]);
-          }
-          const uint32_t row = slot * kStage + w + 4 * r;
-          const size_t off = ((size_t)lane * RBA + row) * 16;
-          *reinterpret_cast<uint4*>(b_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          if (X3) *reinterpret_cast<uint4*>(b_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-          if (row < 7) {                              // wrap copies behind the last ring row
-            const size_t off2 = ((size_t)lane * RBA + RB + row) * 16;
-            *reinterpret_cast<uint4*>(b_hi + off2) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            if (X3) *reinterpret_cast<uint4*>(b_lo + off2) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-          }
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&b_full[slot]);
+      } else {
+        gs += nS; gc += nC;
       }
-      ga += nA; gc += nC;
-    } else if (warp < 12) {
+      gs = __shfl_sync(0xffffffffu, gs, 0);
+      gc = __shfl_sync(0xffffffffu, gc, 0);
+    } else {
       // =============================== epilogue ==============================================
-      const int q = warp - 8;                         // TMEM lane quarter == warp % 4
-      const int row = q * 32 + lane;                  // tile row (feature i0 + row)
+      const int q = warp & 3;                          // TMEM lane quarter this warp may access
+      const int row = q * 32 + lane;                   // tile row (feature i0 + row)
       const uint32_t lane_base = (uint32_t)(q * 32) << 16;
       for (uint32_t c = 0; c < nC; ++c, ++gc) {
         mbar_wait(&acc_full, gc & 1);
@@ -303,140 +228,62 @@ __global__ void __launch_bounds__(kThreads, 1) cov_tc_kernel(const TcParams p) {
 #pragma unroll 1
         for (int which = 0; which < 2; ++which) {
           if (which == 0 ? !do_s0 : !do_st) continue;
-          double* slab = which == 0 ? slab0 : slabt;
-          const uint32_t tbase = (which == 0 ? d0_t : dt_t) + lane_base;
+          const uint32_t src = (which == 0 ? l1_0 : l1_t) + lane_base;
+          const uint32_t dst = (which == 0 ? l2_0 : l2_t) + lane_base;
 #pragma unroll 1
           for (int c0 = 0; c0 < kTile; c0 += 32) {
             uint32_t v[32];
-            tmem_ld_x32(tbase + c0, v);
-            double* sp = slab + (size_t)c0 * kTile + row;
-            if (c == 0) {
+            tmem_ld_x32(src + c0, v);
+            if (c != 0) {
+              uint32_t u[32];
+              tmem_ld_x32(dst + c0, u);
               tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < 32; ++j) sp[(size_t)j * kTile] = (double)__uint_as_float(v[j]);
+              for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
             } else {
-              double old[32];
-#pragma unroll
-              for (int j = 0; j < 32; ++j) old[j] = sp[(size_t)j * kTile];
               tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 32; ++j) sp[(size_t)j * kTile] = old[j] + (double)__uint_as_float(v[j]);
             }
+            tmem_st_x32(dst + c0, v);
           }
         }
+        tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty);
       }
-      // item done: add the FP64 slab into the result (red.global.add.f64, fire and forget)
+      // item done: level 2 -> FP64 result (red.global.add.f64, fire and forget)
       const int gi = i0 + row;
-      if (gi < p.f) {
 #pragma unroll 1
-        for (int which = 0; which < 2; ++which) {
-          if (which == 0 ? !do_s0 : !do_st) continue;
-          const double* slab = which == 0 ? slab0 : slabt;
-          double* out = (which == 0 ? p.S0 : p.St) + (size_t)gi * p.f + j0;
-          const int jn = min(kTile, p.f - j0);
-#pragma unroll 4
-          for (int j = 0; j < jn; ++j) atomicAdd(out + j, slab[(size_t)j * kTile + row]);
-        }
-      }
-      ga += nA; gb += nB;
-    } else {
-      // =============================== MMA issuer ============================================
-      if (lane == 0) {
-        constexpr uint32_t idesc = make_idesc_tf32(kTile, kTile, A_TMEM ? 0 : 1, 1);
-        const uint32_t bh = smem_u32(b_hi), bl = smem_u32(b_lo);
-        const uint32_t ah = smem_u32(a_hi_s), al = smem_u32(a_lo_s);
-        const uint32_t gb0 = gb;
-        uint32_t b_waited = 0;                       // B stages of this item known to be full
-        uint32_t in_chunk = 0;                       // stages issued into the current accumulator chunk
-        for (uint32_t sa = 0; sa < nA; ++sa, ++ga) {
-          const uint32_t slot = ga % NA;
-          if (in_chunk == 0) mbar_wait(&acc_empty, (gc & 1) ^ 1);      // accumulators drained
-          mbar_wait(&a_full[slot], (ga / NA) & 1);
-          uint32_t need = (sa * kStage + kStage - 1 + lag) / kStage;   // last B stage this A stage reads
-          if (need > nB - 1) need = nB - 1;
-          while (b_waited <= need) {
-            const uint32_t g = gb0 + b_waited;
-            mbar_wait(&b_full[g % NB], (g / NB) & 1);
-            ++b_waited;
-          }
-          tc_fence_after();
+      for (int which = 0; which < 2; ++which) {
+        if (which == 0 ? !do_s0 : !do_st) continue;
+        const uint32_t src = (which == 0 ? l2_0 : l2_t) + lane_base;
+        double* out = (which == 0 ? p.S0 : p.St) + (size_t)gi * p.f + j0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < kTile; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_x32(src + c0, v);
+          tmem_ld_wait();
+          if (gi < p.f) {
+            const int jn = p.f - j0 - c0;               // valid columns from c0 on
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const uint32_t u = sa * kStage + h * 8;                    // frame offset inside the item
-            const uint32_t first = (in_chunk == 0 && h == 0) ? 0u : 1u;
-            const uint32_t r0 = ((gb0 + u / kStage) % NB) * kStage + (u % kStage);
-            const uint32_t ul = u + lag;
-            const uint32_t r1 = ((gb0 + ul / kStage) % NB) * kStage + (ul % kStage);
-            const uint64_t b0h = make_smem_desc(bh + r0 * 16, 128, RBA * 16);
-            const uint64_t b0l = make_smem_desc(bl + r0 * 16, 128, RBA * 16);
-            const uint64_t bth = make_smem_desc(bh + r1 * 16, 128, RBA * 16);
-            const uint64_t btl = make_smem_desc(bl + r1 * 16, 128, RBA * 16);
-            if constexpr (A_TMEM) {
-              const uint32_t a_h = a_t + slot * 32 + h * 8, a_l = a_h + 16;
-              if (do_s0) {
-                mma_tf32_ts(d0_t, a_h, b0h, idesc, first);
-                if (X3) { mma_tf32_ts(d0_t, a_h, b0l, idesc, 1); mma_tf32_ts(d0_t, a_l, b0h, idesc, 1); }
-              }
-              if (do_st) {
-                mma_tf32_ts(dt_t, a_h, bth, idesc, first);
-                if (X3) { mma_tf32_ts(dt_t, a_h, btl, idesc, 1); mma_tf32_ts(dt_t, a_l, bth, idesc, 1); }
-              }
-            } else {
-              const uint32_t ar = (slot * kStage + h * 8) * 16;
-              const uint64_t a_h = make_smem_desc(ah + ar, 128, RAA * 16);
-              const uint64_t a_l = make_smem_desc(al + ar, 128, RAA * 16);
-              if (do_s0) {
-                mma_tf32_ss(d0_t, a_h, b0h, idesc, first);
-                if (X3) { mma_tf32_ss(d0_t, a_h, b0l, idesc, 1); mma_tf32_ss(d0_t, a_l, b0h, idesc, 1); }
-              }
-              if (do_st) {
-                mma_tf32_ss(dt_t, a_h, bth, idesc, first);
-                if (X3) { mma_tf32_ss(dt_t, a_h, btl, idesc, 1); mma_tf32_ss(dt_t, a_l, bth, idesc, 1); }
-              }
-            }
-          }
-          mma_commit(&a_empty[slot]);                                  // A stage consumed
-          mma_commit(&b_empty[(gb0 + sa) % NB]);                       // frames < 16(sa+1) are dead
-          if (++in_chunk == kc_stages || sa + 1 == nA) {
-            mma_commit(&acc_full);                                     // accumulators ready to flush
-            in_chunk = 0;
-            ++gc;
+            for (int j = 0; j < 32; ++j)
+              if (j < jn) atomicAdd(out + c0 + j, (double)__uint_as_float(v[j]));
           }
         }
-        // release the look-ahead stages the producer filled beyond the last A stage
-        for (uint32_t sb = nA; sb < nB; ++sb) {
-          const uint32_t g = gb0 + sb;
-          if (sb >= b_waited) mbar_wait(&b_full[g % NB], (g / NB) & 1);
-          mma_commit(&b_empty[g % NB]);
-        }
-        {   // do not run ahead of (or exit before) the last asynchronous release
-          const uint32_t g = gb0 + nB - 1;
-          mbar_wait(&b_empty[g % NB], (g / NB) & 1);
-        }
-        gb = gb0 + nB;
-      } else {
-        ga += nA; gb += nB; gc += nC;
       }
-      // keep the whole warp's counters identical
-      ga = __shfl_sync(0xffffffffu, ga, 0);
-      gb = __shfl_sync(0xffffffffu, gb, 0);
-      gc = __shfl_sync(0xffffffffu, gc, 0);
+      gs += nS;
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 12) tmem_dealloc(tmem, 512);
+  if (warp == kMmaWarp) tmem_dealloc(tmem, 512);
 }
 
 size_t cov_tc_workspace_bytes(int64_t n_rows, int f, int lag, int block, int engine) {
   (void)n_rows; (void)lag; (void)block; (void)engine;
   const size_t nt = (size_t)ceil_div(f, kTile);
-  return 256 + 2 * align_up(nt * nt * sizeof(int), 256) +
-         (size_t)kNumSMs * 2 * kSlabElems * sizeof(double);
+  return 256 + align_up(nt * nt * sizeof(int), 256);
 }
 
 static int env_int(const char* name, int dflt) {
@@ -444,62 +291,50 @@ static int env_int(const char* name, int dflt) {
   return s ? atoi(s) : dflt;
 }
 
-template <bool A_TMEM>
-static int tc_launch_variant(const TcParams& p, bool x3, bool stdz, bool vec4, int grid, cudaStream_t st) {
-  const size_t smem = tc_smem_bytes<A_TMEM>();
-#define DCG_TC_CASE(X3, STD, V4)                                                                    \
-  {                                                                                                 \
-    auto kern = cov_tc_kernel<A_TMEM, X3, STD, V4>;                                                 \
-    DCG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    kern<<<grid, kThreads, smem, st>>>(p);                                                          \
-  }
-  if (x3) {
-    if (stdz) { if (vec4) DCG_TC_CASE(true, true, true) else DCG_TC_CASE(true, true, false) }
-    else { if (vec4) DCG_TC_CASE(true, false, true) else DCG_TC_CASE(true, false, false) }
-  } else {
-    if (stdz) { if (vec4) DCG_TC_CASE(false, true, true) else DCG_TC_CASE(false, true, false) }
-    else { if (vec4) DCG_TC_CASE(false, false, true) else DCG_TC_CASE(false, false, false) }
-  }
-#undef DCG_TC_CASE
-  DCG_LAUNCH_CHECK();
-  return 0;
-}
-
 int cov_tc_launch(const CovArgs& a, cudaStream_t st) {
   int dev = 0, major = 0;
   DCG_CUDA_TRY(cudaGetDevice(&dev));
   DCG_CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
   if (major != 10) return DCG_E_ARCH;
-  const bool a_tmem = env_int("DCG_TC_A_TMEM", 1) != 0;
-  const int max_lag = a_tmem ? tc_max_lag<true>() : tc_max_lag<false>();
-  if (a.lag > max_lag) return cov_simt_launch(a, st);   // lag beyond the frame ring: CUDA-core engine
-  int kc = env_int("DCG_TC_KC", 1024);
+  int kc = env_int("DCG_TC_KC", 128);
   kc = std::max(kStage, kc / kStage * kStage);
 
   const int64_t M = a.n_rows - a.lag;
-  const size_t nt = (size_t)ceil_div(a.f, kTile);
-  char* w = (char*)a.ws;
-  int* counter = (int*)w; w += 256;
-  int* full = (int*)w; w += align_up(nt * nt * sizeof(int), 256);
-  int* half = (int*)w; w += align_up(nt * nt * sizeof(int), 256);
-  double* slabs = (double*)w;
+  const int nt = (int)ceil_div(a.f, kTile);
+  int* d_tiles = (int*)((char*)a.ws + 256);
 
-  std::vector<int> hfull(nt * nt), hhalf(nt * nt);
-  TcPlan plan = tc_make_plan(M, a.f, a.block, a.S0 != nullptr, a.St != nullptr, hfull.data(), hhalf.data());
-  if (plan.n_items == 0) return 0;
-  if (plan.n_full) DCG_CUDA_TRY(cudaMemcpyAsync(full, hfull.data(), plan.n_full * sizeof(int), cudaMemcpyHostToDevice, st));
-  if (plan.n_half) DCG_CUDA_TRY(cudaMemcpyAsync(half, hhalf.data(), plan.n_half * sizeof(int), cudaMemcpyHostToDevice, st));
-  tc_reset_kernel<<<1, 1, 0, st>>>(counter);
+  // needed tiles, the expensive ones (both matrices) first; the list itself is built on the device
+  // (same enumeration) so the launch stays asynchronous
+  int n_tiles = 0;
+  for (int ti = 0; ti < nt; ++ti)
+    for (int tj = 0; tj < nt; ++tj)
+      n_tiles += (a.S0 && tc_tile_needed(ti * kTile, tj * kTile, a.f, a.block, true)) ||
+                 (a.St && tc_tile_needed(ti * kTile, tj * kTile, a.f, a.block, false));
+  if (n_tiles == 0 || M <= 0) return 0;
+  tc_plan_kernel<<<1, 32, 0, st>>>(d_tiles, nt, a.f, a.block, a.S0 != nullptr, a.St != nullptr);
   DCG_LAUNCH_CHECK();
 
-  TcParams p{a.X, a.n_rows, a.ld, a.f, a.lag, a.block, a.mean, a.range, a.S0, a.St,
-             full, half, counter, slabs, plan, kc};
-  const int grid = (int)std::min<int64_t>(kNumSMs, plan.n_items);
+  // frames per work item: ~8 items per SM, a multiple of kc, at most kMaxItemFrames
+  int64_t g = ceil_div(M * n_tiles, (int64_t)kNumSMs * 8);
+  g = std::min<int64_t>(std::max<int64_t>(ceil_div(g, kc) * kc, kc), std::max(kc, kMaxItemFrames / kc * kc));
+  const int64_t n_ranges = ceil_div(M, g);
+
+  TcParams p{a.X, a.n_rows, a.ld, a.f, a.lag, a.mean, a.range, a.S0, a.St,
+             d_tiles, n_tiles, nt, g, n_ranges * n_tiles, kc};
+  const int grid = (int)std::min<int64_t>(kNumSMs, p.n_items);
   const bool x3 = a.engine == DCG_COV_TC_3XTF32;
   const bool stdz = a.mean != nullptr;
-  const bool vec4 = row_vec_width(a.X, a.ld) == 4;
-  return a_tmem ? tc_launch_variant<true>(p, x3, stdz, vec4, grid, st)
-                : tc_launch_variant<false>(p, x3, stdz, vec4, grid, st);
+#define DCG_TC_CASE(X3, STD)                                                                          \
+  {                                                                                                   \
+    auto kern = cov_tc_kernel<X3, STD>;                                                               \
+    DCG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes)); \
+    kern<<<grid, kThreads, kSmemBytes, st>>>(p);                                                      \
+  }
+  if (x3) { if (stdz) DCG_TC_CASE(true, true) else DCG_TC_CASE(true, false) }
+  else { if (stdz) DCG_TC_CASE(false, true) else DCG_TC_CASE(false, false) }
+#undef DCG_TC_CASE
+  DCG_LAUNCH_CHECK();
+  return 0;
 }
 
 }  // namespace dcg

@@ -54,9 +54,11 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 
 // ---- descriptors --------------------------------------------------------------------------------
 // Shared-memory matrix descriptor, SWIZZLE_NONE ("interleave") canonical layout.
-//   MN-major operand, 32-bit elements: element (mn, k) at
-//       start + (mn % 4) * 4 + (k % 8) * 16 + (mn / 4) * SBO + (k / 8) * LBO      [bytes]
-//   i.e. one "core matrix" = 4 MN-elements (16 B) x 8 K-rows, 128 contiguous bytes.
+//   K-major operand, 32-bit elements: element (mn, k) at
+//       start + (k % 4) * 4 + (mn % 8) * 16 + (mn / 8) * SBO + (k / 4) * LBO      [bytes]
+//   i.e. one "core matrix" = 8 MN-rows x 16 B (4 K-elements), 128 contiguous bytes.
+//   (kind::tf32 with MN-major SWIZZLE_NONE operands returned zeros on B200 -- tools_dev/tc_probe.cu --
+//    so only the K-major form is used.)
 // start, lbo, sbo in bytes (multiples of 16).
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t start, uint32_t lbo, uint32_t sbo) {
   uint64_t d = 0;
@@ -126,6 +128,17 @@ __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&v)[
       "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
       ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
         "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+      "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+        "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+        "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }

@@ -36,6 +36,7 @@ struct Params {
   int a_mn;         // SS only: 1 = A stored MN-major, 0 = K-major
   int b_mn;         // 1 = B stored MN-major, 0 = K-major
   int roundtrip;    // 1 = no MMA: tcgen05.st a pattern into D, read it back
+  int a_off;        // TS: extra TMEM column offset of the A operand (alignment probe)
 };
 
 __global__ void __launch_bounds__(128, 1) probe_kernel(Params p) {
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(Params p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
-  const uint32_t a_tmem = tmem + 256;             // TS: A lives at columns [256, 256 + KROWS)
+  const uint32_t a_tmem = tmem + 256 + p.a_off;   // TS: A lives at columns [256 + a_off, ... + KROWS)
 
   if (p.mode == 1) {
     // thread m (lane 32*warp + lane of TMEM) holds A[k][m] for all k
@@ -141,6 +142,55 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(Params p) {
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// TMEM <-> register bandwidth: 4 warps (one per SMSP / lane quarter).
+//  mode 0: tcgen05.ld x32 only; 1: tcgen05.st x32 only; 2: the level-2 drain loop (ld L1, ld L2, add, st L2)
+__global__ void __launch_bounds__(128, 1) tmem_bw_kernel(int mode, int iters, long long* cycles, float* sink) {
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s + ((uint32_t)(warp * 32) << 16);
+  uint32_t v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __float_as_uint((float)(tid + j));
+  for (int c0 = 0; c0 < 512; c0 += 32) tmem_st_x32(tmem + c0, v);
+  tmem_st_wait();
+  __syncthreads();
+  float acc = 0.f;
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    if (mode == 0) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < 256; c0 += 32) { tmem_ld_x32(tmem + c0, v); tmem_ld_wait(); acc += __uint_as_float(v[it & 31]); }
+    } else if (mode == 1) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < 256; c0 += 32) tmem_st_x32(tmem + c0, v);
+      tmem_st_wait();
+    } else {
+#pragma unroll 1
+      for (int c0 = 0; c0 < 256; c0 += 32) {
+        uint32_t u[32];
+        tmem_ld_x32(tmem + c0, v);
+        tmem_ld_x32(tmem + 256 + c0, u);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+        tmem_st_x32(tmem + 256 + c0, v);
+      }
+      tmem_st_wait();
+    }
+  }
+  __syncthreads();
+  const long long t1 = clock64();
+  if (tid == 0) cycles[0] = t1 - t0;
+  sink[tid] = acc + __uint_as_float(v[0]);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base_s, 512);
+}
+
 static float tf32_rn(float x) {   // round-to-nearest-even-ish (rna = ties away) to 10-bit mantissa
   uint32_t u; memcpy(&u, &x, 4);
   u += 0x1000u; u &= 0xFFFFE000u;
@@ -154,7 +204,7 @@ static float tf32_trunc(float x) {
 
 struct Result { double max_abs_err, mean_rel_err, max_rel_err; long long cycles; };
 
-static int g_a_mn = 1, g_b_mn = 1, g_roundtrip = 0, g_verbose = 0;
+static int g_a_mn = 1, g_b_mn = 1, g_roundtrip = 0, g_verbose = 0, g_a_off = 0;
 static Result run(int N, int mode, int shift, int reps, const std::vector<float>& A, const std::vector<float>& B,
                   int ref_round /*0 exact inputs, 1 rn, 2 trunc*/) {
   const int RB = KROWS + PADROWS;
@@ -164,7 +214,7 @@ static Result run(int N, int mode, int shift, int reps, const std::vector<float>
   CK(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice));
   CK(cudaMemset(dD, 0, 128 * N * 4));
-  Params p{dA, dB, dD, dC, N, mode, shift, reps, g_a_mn, g_b_mn, g_roundtrip};
+  Params p{dA, dB, dD, dC, N, mode, shift, reps, g_a_mn, g_b_mn, g_roundtrip, g_a_off};
   const size_t smem = 32 * KROWS * 16 + (size_t)(N / 4) * RB * 16;
   CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   probe_kernel<<<1, 128, smem>>>(p);
@@ -246,6 +296,31 @@ int main() {
     A[0] = 1.f; for (int n = 0; n < N; ++n) B[n] = (float)(n + 1);
     for (int bmn : {0, 1}) { g_b_mn = bmn; Result r = run(N, 0, 0, 1, A, B, 0); printf("hot SS b_mn=%d a_mn=1: err=%g\n", bmn, r.max_abs_err); }
     g_b_mn = 1;
+  }
+  // 0c: TMEM <-> register bandwidth (bytes moved per iteration: 128 lanes x 256 columns x 4 B = 128 KB)
+  {
+    long long* dC; float* dS; CK(cudaMalloc(&dC, 8)); CK(cudaMalloc(&dS, 128 * 4));
+    const char* names[3] = {"ld x32 (256 cols)", "st x32 (256 cols)", "drain: ld L1 + ld L2 + add + st L2 (256 cols)"};
+    for (int mode = 0; mode < 3; ++mode) {
+      tmem_bw_kernel<<<1, 128>>>(mode, 64, dC, dS);
+      CK(cudaDeviceSynchronize());
+      long long cyc; CK(cudaMemcpy(&cyc, dC, 8, cudaMemcpyDeviceToHost));
+      printf("tmem bw %-48s : %.0f cycles per 128 KB pass\n", names[mode], (double)cyc / 64);
+    }
+  }
+  // 0d: TS A operand at unaligned TMEM columns
+  {
+    const int N = 128;
+    std::vector<float> A(KROWS * 128), B((size_t)RB * N);
+    for (auto& v : A) v = (float)(rand() % 17 - 8);
+    for (auto& v : B) v = (float)(rand() % 17 - 8);
+    g_a_mn = 0; g_b_mn = 0;
+    for (int off : {0, 1, 2, 3, 4, 5, 10}) {
+      g_a_off = off;
+      Result r = run(N, 1, 0, 1, A, B, 0);
+      printf("TS a_off=%2d : max_abs_err=%g\n", off, r.max_abs_err);
+    }
+    g_a_off = 0;
   }
   g_verbose = 0;
   g_a_mn = 0; g_b_mn = 0;
