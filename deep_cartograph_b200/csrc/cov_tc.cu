@@ -140,32 +140,38 @@ __global__ void __launch_bounds__(kThreads, 1) cov_tc_kernel(const TcParams p) {
       const int shift = op == 2 ? p.lag : 0;
       // A rows beyond the item's range must be exactly zero; B rows only need to be in bounds
       const int64_t t_lim = op == 0 ? f1 : p.n_rows - shift;
-      float mu = 0.f, rg = 1.f, ri = 1.f;
-      if (STD && col_ok) { mu = p.mean[col]; rg = p.range[col]; ri = 1.0f / rg; }
-      const float* xcol = p.X + (int64_t)shift * p.ld + col;
-      unsigned char* plane_hi = smem + (size_t)(2 * op) * kPlaneBytes + (size_t)row * 16;
-      for (uint32_t s = 0; s < nS; ++s, ++gs) {
+      float mu = 0.f, ri = 1.f;
+      if (STD && col_ok) { mu = p.mean[col]; ri = 1.0f / p.range[col]; }
+      const uint32_t ld32 = (uint32_t)p.ld;          // host guarantees 16 * ld * 4 bytes < 2^32
+      const float* pst = p.X + ((int64_t)shift + f0) * p.ld + col;      // this thread's column at frame f0
+      const uint32_t plane_hi = smem_u32(smem) + (uint32_t)(2 * op) * kPlaneBytes + (uint32_t)row * 16;
+      int64_t t0 = f0;
+      for (uint32_t s = 0; s < nS; ++s, ++gs, t0 += kStage, pst += (size_t)kStage * ld32) {
         const uint32_t slot = gs % kNS;
         if (needed) {
-          const int64_t t0 = f0 + (int64_t)s * kStage;
           float x[kStage];
+          if (col_ok && t0 + kStage <= t_lim) {       // whole stage in bounds: no per-element predicates
 #pragma unroll
-          for (int j = 0; j < kStage; ++j) {
-            const int64_t t = t0 + j;
-            x[j] = (col_ok && t < t_lim) ? __ldg(xcol + t * p.ld) : mu;     // mu -> z == 0 exactly
+            for (int j = 0; j < kStage; ++j) x[j] = __ldg(pst + (size_t)((uint32_t)j * ld32));
+          } else {
+#pragma unroll
+            for (int j = 0; j < kStage; ++j)
+              x[j] = (col_ok && t0 + j < t_lim) ? __ldg(pst + (size_t)((uint32_t)j * ld32)) : mu;   // mu -> z == 0 exactly
           }
           mbar_wait(&empty_bar[slot], ((gs / kNS) & 1) ^ 1);
-          unsigned char* dst = plane_hi + (size_t)slot * kStageBytes;
+          const uint32_t dst = plane_hi + slot * kStageBytes;
 #pragma unroll
           for (int g = 0; g < kStage / 4; ++g) {
             uint32_t hi[4], lo[4];
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
-              const float z = STD ? standardize1(x[4 * g + v], mu, rg, ri) : x[4 * g + v];
-              split_tf32(z, hi[v], lo[v]);
+              // (x - mean) * RN(1/range): within 1 ulp of the reference's IEEE division (the
+              // difference is a per-feature scale factor of at most 1 + 2^-24)
+              const float z = STD ? (x[4 * g + v] - mu) * ri : x[4 * g + v];
+              split_tf32_fast(z, hi[v], lo[v]);
             }
-            *reinterpret_cast<uint4*>(dst + g * kGroupBytes) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            if (X3) *reinterpret_cast<uint4*>(dst + kPlaneBytes + g * kGroupBytes) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            st_shared_v4(dst + g * kGroupBytes, hi[0], hi[1], hi[2], hi[3]);
+            if (X3) st_shared_v4(dst + kPlaneBytes + g * kGroupBytes, lo[0], lo[1], lo[2], lo[3]);
           }
           fence_proxy_async_smem();
         } else {
