@@ -215,11 +215,12 @@ extern "C" int dcg_cov_lag_f32(const float* X, int64_t n_rows, int f, int64_t ld
   if (!ws || ws_bytes < dcg_cov_workspace_bytes(n_rows, f, lag, block, engine)) return DCG_E_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   if (lag == 0) St = nullptr;   // S_tau == S0 when lag == 0: not computed
-  CovArgs a{X, n_rows, f, ld, lag, mean, range, block, S0, St, engine, ws, ws_bytes};
+  CovArgs a{X, n_rows, f, ld, lag, mean, range, block, S0, St, colsum_t, colsum_lag, engine, ws, ws_bytes};
 
   if (colsum_t) DCG_CUDA_TRY(cudaMemsetAsync(colsum_t, 0, (size_t)f * sizeof(double), st));
   if (colsum_lag) DCG_CUDA_TRY(cudaMemsetAsync(colsum_lag, 0, (size_t)f * sizeof(double), st));
-  if (colsum_t || colsum_lag) {
+  // the tcgen05 engine accumulates the column sums inside its diagonal tiles (no extra pass over X)
+  if ((colsum_t || colsum_lag) && (engine == DCG_COV_SIMT_F32 || !cov_tc_fuses_colsums(a))) {
     const int64_t gy = std::min<int64_t>(ceil_div(n_rows, kCsRows), 16384);
     colsum_lag_kernel<<<dim3((unsigned)ceil_div(f, 32), (unsigned)gy), 256, 0, st>>>(
         X, n_rows, f, ld, lag, mean, range, colsum_t, colsum_lag);

@@ -68,6 +68,7 @@ struct TcParams {
   const float* range;
   double* S0;
   double* St;
+  double* colsum;       // [f] sum_{t<M} z_t accumulated by the A producers of diagonal tiles (or null)
   const int* tiles;     // [n_tiles]: (ti * nt + tj) | flags
   int n_tiles, nt;
   int64_t granule;      // frames per work item (multiple of kc)
@@ -88,6 +89,24 @@ __global__ void tc_plan_kernel(int* __restrict__ tiles, int nt, int f, int block
         if ((pass == 0) != (s0 && stt)) continue;
         tiles[n++] = (ti * nt + tj) | (s0 ? kFlagS0 : 0) | (stt ? kFlagSt : 0);
       }
+}
+
+// sum_{t>=lag} z_t = sum_{t<M} z_t - sum_{t<lag} z_t + sum_{t>=M} z_t: 2*lag rows instead of a pass
+// over X.  `sum_t` may be null: then `sum_lag` holds sum_{t<M} z_t on entry.
+__global__ void tc_colsum_lag_kernel(const float* __restrict__ X, int64_t n_rows, int f, int64_t ld, int lag,
+                                     const float* __restrict__ mean, const float* __restrict__ range,
+                                     const double* __restrict__ sum_t, double* __restrict__ sum_lag) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= f) return;
+  float mu = 0.f, ri = 1.f;
+  if (mean) { mu = mean[col]; ri = 1.0f / range[col]; }
+  const int64_t M = n_rows - lag;
+  double head = 0.0, tail = 0.0;
+  for (int64_t t = 0; t < lag; ++t) {
+    head += (double)((X[t * ld + col] - mu) * ri);
+    tail += (double)((X[(M + t) * ld + col] - mu) * ri);
+  }
+  sum_lag[col] = (sum_t ? sum_t[col] : sum_lag[col]) - head + tail;
 }
 
 template <bool X3, bool STD>
@@ -142,87 +161,116 @@ __global__ void __launch_bounds__(kThreads, 1) cov_tc_kernel(const TcParams p) {
       const int64_t t_lim = op == 0 ? f1 : p.n_rows - shift;
       float mu = 0.f, ri = 1.f;
       if (STD && col_ok) { mu = p.mean[col]; ri = 1.0f / p.range[col]; }
+      const bool want_sum = op == 0 && diag && p.colsum != nullptr;      // column sums ride on the diagonal tiles
+      double zsum = 0.0;                             // FP32 within a 16-frame stage, FP64 across stages
       const uint32_t ld32 = (uint32_t)p.ld;          // host guarantees 16 * ld * 4 bytes < 2^32
       const float* pst = p.X + ((int64_t)shift + f0) * p.ld + col;      // this thread's column at frame f0
       const uint32_t plane_hi = smem_u32(smem) + (uint32_t)(2 * op) * kPlaneBytes + (uint32_t)row * 16;
-      int64_t t0 = f0;
-      for (uint32_t s = 0; s < nS; ++s, ++gs, t0 += kStage, pst += (size_t)kStage * ld32) {
-        const uint32_t slot = gs % kNS;
-        if (needed) {
-          float x[kStage];
-          if (col_ok && t0 + kStage <= t_lim) {       // whole stage in bounds: no per-element predicates
+      // 16 frames of this thread's feature -> registers (every load is a coalesced 128-byte row
+      // segment across the warp)
+      auto load_stage = [&](float (&x)[kStage], int64_t t0, const float* pt) {
+        if (col_ok && t0 + kStage <= t_lim) {         // whole stage in bounds: no per-element predicates
 #pragma unroll
-            for (int j = 0; j < kStage; ++j) x[j] = __ldg(pst + (size_t)((uint32_t)j * ld32));
-          } else {
-#pragma unroll
-            for (int j = 0; j < kStage; ++j)
-              x[j] = (col_ok && t0 + j < t_lim) ? __ldg(pst + (size_t)((uint32_t)j * ld32)) : mu;   // mu -> z == 0 exactly
-          }
-          mbar_wait(&empty_bar[slot], ((gs / kNS) & 1) ^ 1);
-          const uint32_t dst = plane_hi + slot * kStageBytes;
-#pragma unroll
-          for (int g = 0; g < kStage / 4; ++g) {
-            uint32_t hi[4], lo[4];
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              // (x - mean) * RN(1/range): within 1 ulp of the reference's IEEE division (the
-              // difference is a per-feature scale factor of at most 1 + 2^-24)
-              const float z = STD ? (x[4 * g + v] - mu) * ri : x[4 * g + v];
-              split_tf32_fast(z, hi[v], lo[v]);
-            }
-            st_shared_v4(dst + g * kGroupBytes, hi[0], hi[1], hi[2], hi[3]);
-            if (X3) st_shared_v4(dst + kPlaneBytes + g * kGroupBytes, lo[0], lo[1], lo[2], lo[3]);
-          }
-          fence_proxy_async_smem();
+          for (int j = 0; j < kStage; ++j) x[j] = __ldg(pt + (size_t)((uint32_t)j * ld32));
         } else {
-          mbar_wait(&empty_bar[slot], ((gs / kNS) & 1) ^ 1);
+#pragma unroll
+          for (int j = 0; j < kStage; ++j)
+            x[j] = (col_ok && t0 + j < t_lim) ? __ldg(pt + (size_t)((uint32_t)j * ld32)) : mu;   // mu -> z == 0 exactly
         }
+      };
+      // standardise, split, store K-major, publish the stage
+      auto emit_stage = [&](const float (&x)[kStage], uint32_t g_stage) {
+        const uint32_t slot = g_stage % kNS;
+        mbar_wait(&empty_bar[slot], ((g_stage / kNS) & 1) ^ 1);
+        const uint32_t dst = plane_hi + slot * kStageBytes;
+        float ssum = 0.f;
+#pragma unroll
+        for (int g = 0; g < kStage / 4; ++g) {
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            // (x - mean) * RN(1/range): within 1 ulp of the reference's IEEE division (the
+            // difference is a per-feature scale factor of at most 1 + 2^-24)
+            const float z = STD ? (x[4 * g + v] - mu) * ri : x[4 * g + v];
+            split_tf32_fast(z, hi[v], lo[v]);
+            if (want_sum) ssum += z;
+          }
+          st_shared_v4(dst + g * kGroupBytes, hi[0], hi[1], hi[2], hi[3]);
+          if (X3) st_shared_v4(dst + kPlaneBytes + g * kGroupBytes, lo[0], lo[1], lo[2], lo[3]);
+        }
+        if (want_sum) zsum += (double)ssum;
+        fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&full_bar[slot]);
+      };
+      if (needed) {
+        // software pipeline: the loads of stage s+1 are in flight while stage s is converted
+        const size_t stage_stride = (size_t)kStage * ld32;
+        float xa[kStage], xb[kStage];
+        int64_t t0 = f0;
+        load_stage(xa, t0, pst);
+        uint32_t s = 0;
+        for (; s + 1 < nS; s += 2) {
+          load_stage(xb, t0 + kStage, pst + stage_stride);
+          emit_stage(xa, gs++);
+          if (s + 2 < nS) load_stage(xa, t0 + 2 * kStage, pst + 2 * stage_stride);
+          emit_stage(xb, gs++);
+          t0 += 2 * kStage;
+          pst += 2 * stage_stride;
+        }
+        if (s < nS) emit_stage(xa, gs++);
+        if (want_sum && col_ok) atomicAdd(p.colsum + col, zsum);
+      } else {
+        for (uint32_t s = 0; s < nS; ++s, ++gs) {
+          const uint32_t slot = gs % kNS;
+          mbar_wait(&empty_bar[slot], ((gs / kNS) & 1) ^ 1);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full_bar[slot]);
+        }
       }
       gc += nC;
     } else if (warp == kMmaWarp) {
       // =============================== MMA issuer ============================================
-      if (lane == 0) {
-        constexpr uint32_t idesc = make_idesc_tf32(kTile, kTile, 0, 0);   // both operands K-major
-        const uint32_t sbase = smem_u32(smem);
-        for (uint32_t s = 0; s < nS; ++s, ++gs) {
-          const uint32_t slot = gs % kNS;
-          const bool chunk_first = (s % chunk_stages) == 0;
-          if (chunk_first) mbar_wait(&acc_empty, (gc & 1) ^ 1);          // level-1 accumulators drained
-          mbar_wait(&full_bar[slot], (gs / kNS) & 1);
-          tc_fence_after();
+      // The whole warp runs the (warp-uniform) control flow; one elected lane issues the tcgen05
+      // instructions, so their operands stay in uniform registers.
+      constexpr uint32_t idesc = make_idesc_tf32(kTile, kTile, 0, 0);   // both operands K-major
+      const uint32_t sbase = smem_u32(smem);
+      uint32_t in_chunk = 0;                                             // stages issued into the current chunk
+      for (uint32_t s = 0; s < nS; ++s, ++gs) {
+        const uint32_t slot = gs % kNS;
+        const bool chunk_first = in_chunk == 0;
+        const bool chunk_last = ++in_chunk == chunk_stages || s + 1 == nS;
+        if (chunk_last) in_chunk = 0;
+        if (chunk_first) mbar_wait(&acc_empty, (gc & 1) ^ 1);          // level-1 accumulators drained
+        mbar_wait(&full_bar[slot], (gs / kNS) & 1);
+        tc_fence_after();
+        if (elect_one_sync()) {
           const uint32_t st_base = sbase + slot * kStageBytes;
+          const uint64_t a_h0 = make_smem_desc(st_base + 0 * kPlaneBytes, kGroupBytes, 128);
+          const uint64_t a_l0 = make_smem_desc(st_base + 1 * kPlaneBytes, kGroupBytes, 128);
+          const uint64_t b_h0 = diag ? a_h0 : make_smem_desc(st_base + 2 * kPlaneBytes, kGroupBytes, 128);
+          const uint64_t b_l0 = diag ? a_l0 : make_smem_desc(st_base + 3 * kPlaneBytes, kGroupBytes, 128);
+          const uint64_t t_h0 = make_smem_desc(st_base + 4 * kPlaneBytes, kGroupBytes, 128);
+          const uint64_t t_l0 = make_smem_desc(st_base + 5 * kPlaneBytes, kGroupBytes, 128);
 #pragma unroll
           for (int h = 0; h < kStage / 8; ++h) {
-            const uint32_t off = (uint32_t)h * 2 * kGroupBytes;             // K = 8 = two 4-frame groups
+            const uint64_t off = (uint64_t)((h * 2 * kGroupBytes) >> 4);     // K = 8 = two 4-frame groups
             const uint32_t acc = (chunk_first && h == 0) ? 0u : 1u;
-            const uint64_t a_h = make_smem_desc(st_base + 0 * kPlaneBytes + off, kGroupBytes, 128);
-            const uint64_t a_l = make_smem_desc(st_base + 1 * kPlaneBytes + off, kGroupBytes, 128);
             if (do_s0) {
-              const uint64_t b_h = diag ? a_h : make_smem_desc(st_base + 2 * kPlaneBytes + off, kGroupBytes, 128);
-              const uint64_t b_l = diag ? a_l : make_smem_desc(st_base + 3 * kPlaneBytes + off, kGroupBytes, 128);
-              mma_tf32_ss(l1_0, a_h, b_h, idesc, acc);
-              if (X3) { mma_tf32_ss(l1_0, a_h, b_l, idesc, 1); mma_tf32_ss(l1_0, a_l, b_h, idesc, 1); }
+              mma_tf32_ss(l1_0, a_h0 + off, b_h0 + off, idesc, acc);
+              if (X3) { mma_tf32_ss(l1_0, a_h0 + off, b_l0 + off, idesc, 1); mma_tf32_ss(l1_0, a_l0 + off, b_h0 + off, idesc, 1); }
             }
             if (do_st) {
-              const uint64_t b_h = make_smem_desc(st_base + 4 * kPlaneBytes + off, kGroupBytes, 128);
-              const uint64_t b_l = make_smem_desc(st_base + 5 * kPlaneBytes + off, kGroupBytes, 128);
-              mma_tf32_ss(l1_t, a_h, b_h, idesc, acc);
-              if (X3) { mma_tf32_ss(l1_t, a_h, b_l, idesc, 1); mma_tf32_ss(l1_t, a_l, b_h, idesc, 1); }
+              mma_tf32_ss(l1_t, a_h0 + off, t_h0 + off, idesc, acc);
+              if (X3) { mma_tf32_ss(l1_t, a_h0 + off, t_l0 + off, idesc, 1); mma_tf32_ss(l1_t, a_l0 + off, t_h0 + off, idesc, 1); }
             }
           }
           mma_commit(&empty_bar[slot]);                                    // stage consumed
-          if ((s + 1) % chunk_stages == 0 || s + 1 == nS) {
-            mma_commit(&acc_full);                                         // chunk ready to drain
-            ++gc;
-          }
+          if (chunk_last) mma_commit(&acc_full);                           // chunk ready to drain
         }
-      } else {
-        gs += nS; gc += nC;
+        __syncwarp();
+        if (chunk_last) ++gc;
       }
-      gs = __shfl_sync(0xffffffffu, gs, 0);
-      gc = __shfl_sync(0xffffffffu, gc, 0);
     } else {
       // =============================== epilogue ==============================================
       const int q = warp & 3;                          // TMEM lane quarter this warp may access
@@ -325,7 +373,8 @@ int cov_tc_launch(const CovArgs& a, cudaStream_t st) {
   g = std::min<int64_t>(std::max<int64_t>(ceil_div(g, kc) * kc, kc), std::max(kc, kMaxItemFrames / kc * kc));
   const int64_t n_ranges = ceil_div(M, g);
 
-  TcParams p{a.X, a.n_rows, a.ld, a.f, a.lag, a.mean, a.range, a.S0, a.St,
+  double* colsum = a.colsum_t ? a.colsum_t : a.colsum_lag;      // sum_{t<M} z_t lands here first
+  TcParams p{a.X, a.n_rows, a.ld, a.f, a.lag, a.mean, a.range, a.S0, a.St, colsum,
              d_tiles, n_tiles, nt, g, n_ranges * n_tiles, kc};
   const int grid = (int)std::min<int64_t>(kNumSMs, p.n_items);
   const bool x3 = a.engine == DCG_COV_TC_3XTF32;
@@ -340,7 +389,14 @@ int cov_tc_launch(const CovArgs& a, cudaStream_t st) {
   else { if (stdz) DCG_TC_CASE(false, true) else DCG_TC_CASE(false, false) }
 #undef DCG_TC_CASE
   DCG_LAUNCH_CHECK();
+  if (a.colsum_lag) {
+    tc_colsum_lag_kernel<<<(unsigned)ceil_div(a.f, 128), 128, 0, st>>>(
+        a.X, a.n_rows, a.f, a.ld, a.lag, a.mean, a.range, a.colsum_t, a.colsum_lag);
+    DCG_LAUNCH_CHECK();
+  }
   return 0;
 }
+
+bool cov_tc_fuses_colsums(const CovArgs& a) { return a.n_rows - a.lag > 0; }
 
 }  // namespace dcg
