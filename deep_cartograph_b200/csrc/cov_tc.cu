@@ -37,6 +37,8 @@ namespace dcg {
 
 using namespace tc;
 
+namespace v1 {
+
 constexpr int kTile = 128;           // UMMA M = N = 128 features
 constexpr int kStage = 16;           // frames per pipeline stage (two K = 8 MMA steps)
 constexpr int kNS = 4;               // pipeline stages
@@ -334,7 +336,10 @@ __global__ void __launch_bounds__(kThreads, 1) cov_tc_kernel(const TcParams p) {
   if (warp == kMmaWarp) tmem_dealloc(tmem, 512);
 }
 
-size_t cov_tc_workspace_bytes(int64_t n_rows, int f, int lag, int block, int engine) {
+}  // namespace v1
+using namespace v1;
+
+size_t cov_tc1_workspace_bytes(int64_t n_rows, int f, int lag, int block, int engine) {
   (void)n_rows; (void)lag; (void)block; (void)engine;
   const size_t nt = (size_t)ceil_div(f, kTile);
   return 256 + align_up(nt * nt * sizeof(int), 256);
@@ -345,7 +350,7 @@ static int env_int(const char* name, int dflt) {
   return s ? atoi(s) : dflt;
 }
 
-int cov_tc_launch(const CovArgs& a, cudaStream_t st) {
+int cov_tc1_launch(const CovArgs& a, cudaStream_t st) {
   int dev = 0, major = 0;
   DCG_CUDA_TRY(cudaGetDevice(&dev));
   DCG_CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
@@ -397,6 +402,6 @@ int cov_tc_launch(const CovArgs& a, cudaStream_t st) {
   return 0;
 }
 
-bool cov_tc_fuses_colsums(const CovArgs& a) { return a.n_rows - a.lag > 0; }
+bool cov_tc1_fuses_colsums(const CovArgs& a) { return a.n_rows - a.lag > 0; }
 
 }  // namespace dcg
