@@ -29,7 +29,7 @@
 //
 // Persistent clusters (one CTA per SM, static strided work-item schedule), warp-specialised roles
 // joined by mbarrier pipelines:  warps 0-15 producers (two sets of 4 A + 4 B warps, alternating
-// stages) | 16 MMA issuer (leader CTA) | 17-20 epilogue.  "full" / "accumulator drained" barriers live in the leader CTA and are arrived on
+// stages) | 16-19 epilogue, warp 16 of the leader CTA also issuing the MMAs.  "full" / "accumulator drained" barriers live in the leader CTA and are arrived on
 // remotely by the peer; "stage free" / "accumulator ready" are tcgen05.commit multicasts.
 //
 // Roofline: tensor pipe.  Algorithmic work 3*F^2 FLOP per frame pair (2F^2 for St + F^2 for the
@@ -55,7 +55,7 @@ constexpr int kSetWarps = 8;         // warps per set: 4 per operand (one per 4-
 constexpr int kProdWarps = kSets * kSetWarps;
 constexpr int kEpiWarps = 4;
 constexpr int kMmaWarp = kProdWarps;
-constexpr int kThreads = (kProdWarps + 1 + kEpiWarps) * 32;   // 672
+constexpr int kThreads = (kProdWarps + kEpiWarps) * 32;       // 640: 5 warps per scheduler, 96 registers
 constexpr int kGroupBytes = kHalf * 16;                       // one 4-frame group of 128 rows
 constexpr int kPlaneBytes = (kStage / 4) * kGroupBytes;       // 8 KB: one operand plane (hi or lo)
 constexpr int kStageBytes = 4 * kPlaneBytes;                  // A_hi A_lo B_hi B_lo
@@ -251,40 +251,42 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) cov_tc2
       const int op = (warp >> 2) & 1;                  // 0 = A (z_t[I]), 1 = B (z_t[J] or z_{t+lag}[J])
       const int g = warp & 3;                          // 4-frame group of the stage
       const bool needed = op == 0 || !td.diag;
-      if (needed) {
-        const int c = (op == 0 ? td.i0 : td.j0) + (int)rank * kHalf + 4 * lane;   // first of 4 features
-        const int c_lo = op == 0 ? td.i_lo : td.j_lo, c_hi = op == 0 ? td.i_hi : td.j_hi;
-        const bool all_ok = c >= c_lo && c + 3 < c_hi;
-        bool ok[4];
-        float mu[4], ri[4];
+      const int c = (op == 0 ? td.i0 : td.j0) + (int)rank * kHalf + 4 * lane;   // first of 4 features
+      const int c_lo = op == 0 ? td.i_lo : td.j_lo, c_hi = op == 0 ? td.i_hi : td.j_hi;
+      const bool all_ok = c >= c_lo && c + 3 < c_hi;
+      bool ok[4];
+      float mu[4], ri[4];
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          ok[v] = c + v >= c_lo && c + v < c_hi;
-          mu[v] = 0.f; ri[v] = 1.f;
-          if (ok[v] && p.mean) { mu[v] = p.mean[c + v]; ri[v] = 1.0f / p.range[c + v]; }
+      for (int v = 0; v < 4; ++v) {
+        ok[v] = c + v >= c_lo && c + v < c_hi;
+        mu[v] = 0.f; ri[v] = 1.f;
+        if (ok[v] && p.mean) { mu[v] = p.mean[c + v]; ri[v] = 1.0f / p.range[c + v]; }
+      }
+      const int shift = (op == 1 && td.kind == 1) ? p.lag : 0;
+      // frames are counted from the item start f0.  A rows beyond the item's range must be exactly
+      // zero (also what the column sums need); B rows only need to be in bounds.
+      const int t_lim = (int)((op == 0 || td.diag ? f1 : p.n_rows - shift) - f0);
+      const size_t ld = (size_t)p.ld;
+      const float* pst = p.X + (size_t)(f0 + shift + set * kStage + 4 * g) * ld + c;   // this thread's first block
+      // x[4 * r + v] = frame (t0 + r), feature (c + v)
+      auto load_block = [&](float (&x)[16], int t0, const float* pt) {
+        if (all_ok && t0 + 3 < t_lim) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) load_row4<VEC>(pt + r * ld, &x[4 * r]);
+        } else {
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int v = 0; v < 4; ++v)
+              x[4 * r + v] = (ok[v] && t0 + r < t_lim) ? __ldg(pt + r * ld + v) : mu[v];   // mu -> z == 0 exactly
         }
-        const int shift = (op == 1 && td.kind == 1) ? p.lag : 0;
-        // A rows beyond the item's range must be exactly zero; B rows only need to be in bounds
-        const int64_t t_lim = op == 0 ? f1 : p.n_rows - shift;
-        const bool want_sum = op == 0 && td.diag && p.colsum != nullptr;   // column sums ride on the diagonal tiles
-        double zsum[4] = {0.0, 0.0, 0.0, 0.0};
-        const size_t ld = (size_t)p.ld;
-        const float* pst = p.X + (size_t)(f0 + shift + set * kStage + 4 * g) * ld + c;   // this thread's first block
+      };
+      constexpr int kStep = kSets * kStage;                 // frames between this warp's stages
+      const size_t step_stride = (size_t)kStep * ld;
+      int t0 = set * kStage + 4 * g;
+      uint32_t s = (uint32_t)set;
+      if (needed) {
         const uint32_t dst0 = smem_base + (uint32_t)(2 * op) * kPlaneBytes + (uint32_t)g * kGroupBytes + (uint32_t)lane * 16;
-
-        // x[4 * r + v] = frame (t0 + r), feature (c + v)
-        auto load_block = [&](float (&x)[16], int64_t t0, const float* pt) {
-          if (all_ok && t0 + 3 < t_lim) {
-#pragma unroll
-            for (int r = 0; r < 4; ++r) load_row4<VEC>(pt + r * ld, &x[4 * r]);
-          } else {
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-#pragma unroll
-              for (int v = 0; v < 4; ++v)
-                x[4 * r + v] = (ok[v] && t0 + r < t_lim) ? __ldg(pt + r * ld + v) : mu[v];   // mu -> z == 0 exactly
-          }
-        };
         // standardise, split, store K-major, publish the stage
         auto emit_block = [&](const float (&x)[16], uint32_t g_stage) {
           const uint32_t slot = g_stage % kNS;
@@ -306,23 +308,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) cov_tc2
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive_cta(&full_bar[slot], 0);
-          if (want_sum) {          // diagonal S0 tiles only; kept off the common path (FP64 adds are slow)
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              float s = 0.f;
-#pragma unroll
-              for (int r = 0; r < 4; ++r) s += (x[4 * r + v] - mu[v]) * ri[v];
-              zsum[v] += (double)s;
-            }
-          }
         };
         // software pipeline: the loads of this warp's next stage are in flight while the current one
-        // is converted (and the other warp sets work on the stages in between)
-        constexpr int kStep = kSets * kStage;                 // frames between this warp's stages
-        const size_t step_stride = (size_t)kStep * ld;
+        // is converted (and the other warp set works on the stages in between)
         float xa[16], xb[16];
-        int64_t t0 = f0 + set * kStage + 4 * g;
-        uint32_t s = (uint32_t)set;
         if (s < nS) load_block(xa, t0, pst);
         for (; s + kSets < nS; s += 2 * kSets) {
           load_block(xb, t0 + kStep, pst + step_stride);
@@ -333,80 +322,92 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) cov_tc2
           pst += 2 * step_stride;
         }
         if (s < nS) emit_block(xa, gs + s);
-        gs += nS;
+      } else {
+        // Diagonal S0 tile: B is A, so the B warps have nothing to stage.  They keep the pipeline
+        // protocol and, if asked, accumulate the column sums sum_t z_t of the tile's features (same
+        // rows and bounds as the A operand) -- FP32 within a 4-frame block, FP64 across blocks.
+        const bool want_sum = p.colsum != nullptr;
+        double zsum[4] = {0.0, 0.0, 0.0, 0.0};
+        for (; s < nS; s += kSets, t0 += kStep, pst += step_stride) {
+          const uint32_t slot = (gs + s) % kNS;
+          mbar_wait(&empty_bar[slot], (((gs + s) / kNS) & 1) ^ 1);
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cta(&full_bar[slot], 0);
+          if (want_sum) {
+            float x[16];
+            load_block(x, t0, pst);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              float sv = 0.f;
+#pragma unroll
+              for (int r = 0; r < 4; ++r) sv += (x[4 * r + v] - mu[v]) * ri[v];
+              zsum[v] += (double)sv;
+            }
+          }
+        }
         if (want_sum) {
 #pragma unroll
           for (int v = 0; v < 4; ++v)
             if (ok[v]) atomicAdd(p.colsum + c + v, zsum[v]);
         }
-      } else {
-        for (uint32_t s = (uint32_t)set; s < nS; s += kSets) {
-          const uint32_t slot = (gs + s) % kNS;
-          mbar_wait(&empty_bar[slot], (((gs + s) / kNS) & 1) ^ 1);
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cta(&full_bar[slot], 0);
-        }
-        gs += nS;
       }
+      gs += nS;
       gc += nC;
-    } else if (warp == kMmaWarp) {
-      // =============================== MMA issuer (leader CTA) ================================
-      if (rank == 0) {
-        constexpr uint32_t idesc = make_idesc_tf32(kSup, kSup, 0, 0);   // both operands K-major
-        uint32_t in_chunk = 0;                                           // stages issued into the current chunk
-        for (uint32_t s = 0; s < nS; ++s, ++gs) {
-          const uint32_t slot = gs % kNS;
-          const bool chunk_first = in_chunk == 0;
-          const bool chunk_last = ++in_chunk == chunk_stages || s + 1 == nS;
-          if (chunk_last) in_chunk = 0;
-          if (chunk_first) mbar_wait_cluster(&acc_empty, (gc & 1) ^ 1);  // level 1 drained in both CTAs
-          mbar_wait_cluster(&full_bar[slot], (gs / kNS) & 1);
-          tc_fence_after();
-          if (elect_one_sync()) {
-            const uint32_t st_base = smem_base + slot * kStageBytes;
-            const uint64_t a_h0 = make_smem_desc(st_base + 0 * kPlaneBytes, kGroupBytes, 128);
-            const uint64_t a_l0 = make_smem_desc(st_base + 1 * kPlaneBytes, kGroupBytes, 128);
-            const uint64_t b_h0 = td.diag ? a_h0 : make_smem_desc(st_base + 2 * kPlaneBytes, kGroupBytes, 128);
-            const uint64_t b_l0 = td.diag ? a_l0 : make_smem_desc(st_base + 3 * kPlaneBytes, kGroupBytes, 128);
-#pragma unroll
-            for (int h = 0; h < kStage / 8; ++h) {
-              const uint64_t off = (uint64_t)((h * 2 * kGroupBytes) >> 4);     // K = 8 = two 4-frame groups
-              mma2_tf32_ss(l1, a_h0 + off, b_h0 + off, idesc, (chunk_first && h == 0) ? 0u : 1u);
-              if (X3) {
-                mma2_tf32_ss(l1, a_h0 + off, b_l0 + off, idesc, 1);
-                mma2_tf32_ss(l1, a_l0 + off, b_h0 + off, idesc, 1);
-              }
-            }
-            mma2_commit_both(&empty_bar[slot]);                              // stage consumed
-            if (chunk_last) mma2_commit_both(&acc_full);                     // chunk ready to drain
-          }
-          __syncwarp();
-          if (chunk_last) ++gc;
-        }
-      } else {
-        gs += nS; gc += nC;
-      }
     } else {
-      // =============================== epilogue ==============================================
+      // ============ epilogue warps; the first one of the leader CTA also issues the MMAs ========
+      // Level 1 is single-buffered, so MMA issue and accumulator drain of one CTA pair strictly
+      // alternate: one warp can do both (issue the chunk's stages, wait for them to complete, drain
+      // its lane quarter), which keeps the CTA at 20 warps = 96 registers per thread.
       const int q = warp & 3;                          // TMEM lane quarter this warp may access
       const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+      const bool issuer = warp == kMmaWarp && rank == 0;
+      constexpr uint32_t idesc = make_idesc_tf32(kSup, kSup, 0, 0);   // both operands K-major
+      uint32_t s = 0;
       for (uint32_t c = 0; c < nC; ++c, ++gc) {
+        if (issuer) {
+          mbar_wait_cluster(&acc_empty, (gc & 1) ^ 1);                   // level 1 drained in both CTAs
+          const uint32_t s_end = s + chunk_stages < nS ? s + chunk_stages : nS;
+          for (bool first = true; s < s_end; ++s, first = false) {
+            const uint32_t slot = (gs + s) % kNS;
+            mbar_wait_cluster(&full_bar[slot], ((gs + s) / kNS) & 1);
+            tc_fence_after();
+            if (elect_one_sync()) {
+              const uint32_t st_base = smem_base + slot * kStageBytes;
+              const uint64_t a_h0 = make_smem_desc(st_base + 0 * kPlaneBytes, kGroupBytes, 128);
+              const uint64_t a_l0 = make_smem_desc(st_base + 1 * kPlaneBytes, kGroupBytes, 128);
+              const uint64_t b_h0 = td.diag ? a_h0 : make_smem_desc(st_base + 2 * kPlaneBytes, kGroupBytes, 128);
+              const uint64_t b_l0 = td.diag ? a_l0 : make_smem_desc(st_base + 3 * kPlaneBytes, kGroupBytes, 128);
+#pragma unroll
+              for (int h = 0; h < kStage / 8; ++h) {
+                const uint64_t off = (uint64_t)((h * 2 * kGroupBytes) >> 4);     // K = 8 = two 4-frame groups
+                mma2_tf32_ss(l1, a_h0 + off, b_h0 + off, idesc, (first && h == 0) ? 0u : 1u);
+                if (X3) {
+                  mma2_tf32_ss(l1, a_h0 + off, b_l0 + off, idesc, 1);
+                  mma2_tf32_ss(l1, a_l0 + off, b_h0 + off, idesc, 1);
+                }
+              }
+              mma2_commit_both(&empty_bar[slot]);                              // stage consumed
+              if (s + 1 == s_end) mma2_commit_both(&acc_full);                 // chunk ready to drain
+            }
+            __syncwarp();
+          }
+        }
         mbar_wait(&acc_full, gc & 1);
         tc_fence_after();
 #pragma unroll 1
-        for (int c0 = 0; c0 < kSup; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld_x16(l1 + lane_base + c0, v);
+        for (int c0 = 0; c0 < kSup; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_x32(l1 + lane_base + c0, v);
           if (c != 0) {
-            uint32_t u[16];
-            tmem_ld_x16(l2 + lane_base + c0, u);
+            uint32_t u[32];
+            tmem_ld_x32(l2 + lane_base + c0, u);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
           } else {
             tmem_ld_wait();
           }
-          tmem_st_x16(l2 + lane_base + c0, v);
+          tmem_st_x32(l2 + lane_base + c0, v);
         }
         tmem_st_wait();
         tc_fence_before();
