@@ -206,8 +206,23 @@ def main():
     torch.cuda.synchronize()
 
     cov_ev = []
+    pass_ev = {k: [] for k in ("stats", "covariance", "eigen", "projection", "kmeans")}
+
+    class _Timed:
+        """CUDA-event bracket around one pass (on torch's current stream, where the kernels launch)."""
+        def __init__(self, name, on):
+            self.name, self.on = name, on
+        def __enter__(self):
+            if self.on:
+                self.e0 = torch.cuda.Event(enable_timing=True); self.e1 = torch.cuda.Event(enable_timing=True)
+                self.e0.record()
+        def __exit__(self, *a):
+            if self.on:
+                self.e1.record()
+                pass_ev[self.name].append((self.e0, self.e1))
 
     def step(record=False):
+      with _Timed("stats", record):
         st = ops.column_stats(X)
         if shards is not None:
             st = shards.merge_stats(st)
@@ -215,6 +230,7 @@ def main():
         mean = st["mean"].to(torch.float32)
         rng = torch.sqrt(st["m2"] / (ntot - 1)).to(torch.float32)
         rng = torch.where(rng.abs() < 1e-8, torch.ones_like(rng), rng)
+      with _Timed("covariance", record):
         Xh = shards.with_halo(X, LAG) if shards is not None else X
         if record:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -225,12 +241,15 @@ def main():
             cov_ev.append((e0, e1))
         if shards is not None:
             s = shards.allreduce_sums(s)
+      with _Timed("eigen", record):
         evals, V = linalg.tica_from_sums(ops.symmetrize_upper(s["S0"]), s["St"], s["a"], s["b"], s["M"], DIM)
         W = V.to(torch.float32)
+      with _Timed("projection", record):
         P, pmin, pmax = ops.project(X, W, mean, rng)
         if shards is not None:
             pmin, pmax = shards.allreduce_minmax(pmin, pmax)
         ops.standardize_(P, (pmax + pmin) / 2, (pmax - pmin) / 2)
+      with _Timed("kmeans", record):
         # KMeans: fixed init = first K projected frames of rank 0, fixed number of Lloyd iterations
         C = P[:K].to(torch.float64).clone()
         if shards is not None:
@@ -244,7 +263,7 @@ def main():
                 sums, counts = packed[:K * DIM].view(K, DIM), packed[K * DIM:]
             nz = counts > 0
             C = torch.where(nz[:, None], sums / counts.clamp(min=1.0)[:, None], C)
-        return evals, labels
+      return evals, labels
 
     def sync_all():
         torch.cuda.synchronize()
@@ -288,6 +307,26 @@ def main():
                 "kernel_ms": cov_s * 1e3, "share_of_step": cov_s * 1e3 / ms_per_step,
                 "peak_source": f"{peaks['source']} bf16 burst / 2 (TF32 : bf16 = 1 : 2 on tcgen05)",
                 "algorithmic": "3*F^2 FLOP per frame pair; issued = x3 for 3xTF32"}
+
+    # ---- per-pass device times and the HBM fractions of the memory-bound passes (SURVEY 8d bytes)
+    def _avg_ms(name):
+        ev = pass_ev[name]
+        return sum(a.elapsed_time(b) for a, b in ev) / max(1, len(ev))
+    hbm = peaks["hbm_gbs"]
+    pm = {k: _avg_ms(k) for k in pass_ev}
+    passes = {
+        "stats": {"ms": pm["stats"], "alg_bytes": 4.0 * f * n, "bound": "hbm"},
+        "covariance": {"ms": pm["covariance"], "bound": "tensor", "note": "kernel alone: roofline.kernel_ms"},
+        "eigen": {"ms": pm["eigen"], "bound": "none (F x F FP64 eigenproblem, cuSOLVER)"},
+        "projection": {"ms": pm["projection"], "alg_bytes": (4.0 * f + 4.0 * DIM) * n + 8.0 * DIM * n, "bound": "hbm",
+                       "note": "4F read + 4d written per frame, + 8d for the in-place CV normalisation"},
+        "kmeans": {"ms": pm["kmeans"], "alg_bytes": KM_ITERS * (4.0 * DIM + 4.0) * n, "bound": "hbm (k small)",
+                   "iters": KM_ITERS},
+    }
+    for v in passes.values():
+        if "alg_bytes" in v:
+            v["gbs"] = v["alg_bytes"] / (v["ms"] * 1e-3) / 1e9
+            v["frac_hbm"] = v["gbs"] / hbm
 
     # ---- e2e through the public API with host buffers
     e2e = None
@@ -338,7 +377,7 @@ def main():
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32 (tf32x3 tensor contraction, f64 accumulation)" if engine == "tc_3xtf32" else "f32",
                 "data": "synthetic", "config": workload_config(args, world, engine),
-                "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
+                "roofline": roofline, "passes": passes, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
                 "clocks": clocks, "eigenvalues": [float(v) for v in evals.cpu().tolist()]}
         print(json.dumps(line), flush=True)
     if shards is not None:

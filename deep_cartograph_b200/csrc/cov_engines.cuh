@@ -27,9 +27,5 @@ int cov_simt_launch(const CovArgs& a, cudaStream_t st);
 int cov_tc_launch(const CovArgs& a, cudaStream_t st);
 bool cov_tc_fuses_colsums(const CovArgs& a);
 size_t cov_tc_workspace_bytes(int64_t n_rows, int f, int lag, int block, int engine);
-// first-generation single-CTA 128 x 128 engine (DCG_TC_IMPL=1; kept for A/B measurements)
-int cov_tc1_launch(const CovArgs& a, cudaStream_t st);
-bool cov_tc1_fuses_colsums(const CovArgs& a);
-size_t cov_tc1_workspace_bytes(int64_t n_rows, int f, int lag, int block, int engine);
 
 }  // namespace dcg
