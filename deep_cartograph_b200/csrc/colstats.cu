@@ -13,7 +13,6 @@ namespace dcg {
 
 constexpr int kStatWarps = 8;
 constexpr int kStatThreads = kStatWarps * 32;
-constexpr int kStatRowsPerCta = 1024;
 constexpr int kStatUnroll = 4;
 
 struct StatPartial {  // one per (row block, column)
@@ -36,13 +35,13 @@ __device__ __forceinline__ void load_vec(const float* p, float (&v)[VEC]) {
 
 template <int VEC>
 __global__ void __launch_bounds__(kStatThreads)
-colstats_partial_kernel(const float* __restrict__ X, int64_t n, int f, int64_t ld,
+colstats_partial_kernel(const float* __restrict__ X, int64_t n, int f, int64_t ld, int64_t rows_per_cta,
                         StatPartial* __restrict__ part, float* __restrict__ pmin,
                         float* __restrict__ pmax) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int col0 = (blockIdx.x * 32 + lane) * VEC;            // first column of this thread
-  const int64_t row_begin = (int64_t)blockIdx.y * kStatRowsPerCta;
-  const int64_t row_end = min(n, row_begin + kStatRowsPerCta);
+  const int64_t row_begin = (int64_t)blockIdx.y * rows_per_cta;
+  const int64_t row_end = min(n, row_begin + rows_per_cta);
   const bool active = col0 < f;                                // f % VEC == 0 guaranteed by host
 
   // Shifted sums: d = x - K with K = the tile's first row of this column, so every FP32 quantity
@@ -153,7 +152,7 @@ colstats_partial_kernel(const float* __restrict__ X, int64_t n, int f, int64_t l
 // One thread per column: sequential Chan merge over row blocks (coalesced across columns).
 __global__ void colstats_merge_kernel(const StatPartial* __restrict__ part,
                                       const float* __restrict__ pmin, const float* __restrict__ pmax,
-                                      int64_t n, int f, int row_blocks,
+                                      int64_t n, int f, int row_blocks, int64_t rows_per_cta,
                                       double* __restrict__ mean, double* __restrict__ m2,
                                       float* __restrict__ minv, float* __restrict__ maxv) {
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
@@ -161,8 +160,8 @@ __global__ void colstats_merge_kernel(const StatPartial* __restrict__ part,
   double na = 0.0, ma = 0.0, qa = 0.0;
   float lo = INFINITY, hi = -INFINITY;
   for (int b = 0; b < row_blocks; ++b) {
-    const int64_t r0 = (int64_t)b * kStatRowsPerCta;
-    const double nb = (double)min((int64_t)kStatRowsPerCta, n - r0);
+    const int64_t r0 = (int64_t)b * rows_per_cta;
+    const double nb = (double)min(rows_per_cta, n - r0);
     const StatPartial p = part[(size_t)b * f + col];
     const double nt = na + nb, dl = p.mean - ma;
     ma += dl * (nb / nt);
@@ -181,9 +180,18 @@ __global__ void colstats_merge_kernel(const StatPartial* __restrict__ part,
 
 using namespace dcg;
 
+// Rows per CTA: ~8 CTAs per SM over the (column strip) x (row block) grid, so that the per-block
+// partials stay tiny (the merge walks them sequentially per column) and HBM sees long row streams.
+static int64_t stat_rows_per_cta(int64_t n, int f) {
+  const int64_t strips = ceil_div(f, 128);
+  const int64_t want_blocks = std::max<int64_t>(1, ceil_div((int64_t)kNumSMs * 8, strips));
+  const int64_t step = (int64_t)kStatWarps * kStatUnroll;
+  return std::max<int64_t>(8 * step, ceil_div(ceil_div(n, want_blocks), step) * step);
+}
+
 extern "C" size_t dcg_colstats_workspace_bytes(int64_t n, int f) {
   if (n <= 0 || f <= 0) return 0;
-  const size_t rb = (size_t)ceil_div(n, kStatRowsPerCta);
+  const size_t rb = (size_t)ceil_div(n, stat_rows_per_cta(n, f));
   return align_up(rb * f * sizeof(StatPartial), 256) + 2 * align_up(rb * f * sizeof(float), 256);
 }
 
@@ -194,11 +202,8 @@ extern "C" int dcg_colstats_f32(const float* X, int64_t n, int f, int64_t ld,
   if (n <= 0 || f <= 0 || ld < f) return DCG_E_SHAPE;
   if (!ws || ws_bytes < dcg_colstats_workspace_bytes(n, f)) return DCG_E_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
-  const int rb = (int)ceil_div(n, kStatRowsPerCta);
-  if (rb > 65535) {
-    // grid.y limit: 65535 * 1024 rows = 67M frames per call; callers chunk beyond that
-    return DCG_E_SHAPE;
-  }
+  const int64_t rpc = stat_rows_per_cta(n, f);
+  const int rb = (int)ceil_div(n, rpc);
   char* w = (char*)ws;
   StatPartial* part = (StatPartial*)w;
   w += align_up((size_t)rb * f * sizeof(StatPartial), 256);
@@ -209,13 +214,13 @@ extern "C" int dcg_colstats_f32(const float* X, int64_t n, int f, int64_t ld,
   while (f % vec) vec >>= 1;
   dim3 grid((unsigned)ceil_div(f, 32 * vec), (unsigned)rb);
   if (vec == 4)
-    colstats_partial_kernel<4><<<grid, kStatThreads, 0, st>>>(X, n, f, ld, part, pmin, pmax);
+    colstats_partial_kernel<4><<<grid, kStatThreads, 0, st>>>(X, n, f, ld, rpc, part, pmin, pmax);
   else if (vec == 2)
-    colstats_partial_kernel<2><<<grid, kStatThreads, 0, st>>>(X, n, f, ld, part, pmin, pmax);
+    colstats_partial_kernel<2><<<grid, kStatThreads, 0, st>>>(X, n, f, ld, rpc, part, pmin, pmax);
   else
-    colstats_partial_kernel<1><<<grid, kStatThreads, 0, st>>>(X, n, f, ld, part, pmin, pmax);
+    colstats_partial_kernel<1><<<grid, kStatThreads, 0, st>>>(X, n, f, ld, rpc, part, pmin, pmax);
   DCG_LAUNCH_CHECK();
-  colstats_merge_kernel<<<(unsigned)ceil_div(f, 128), 128, 0, st>>>(part, pmin, pmax, n, f, rb,
+  colstats_merge_kernel<<<(unsigned)ceil_div(f, 128), 128, 0, st>>>(part, pmin, pmax, n, f, rb, rpc,
                                                                     mean, m2, minv, maxv);
   DCG_LAUNCH_CHECK();
   return 0;

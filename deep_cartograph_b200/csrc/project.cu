@@ -13,12 +13,31 @@ namespace dcg {
 constexpr int kProjWarps = 8;
 constexpr int kProjThreads = kProjWarps * 32;
 
+// Per-column operands laid out for coalesced loads in the main kernel (a lane owns VEC consecutive
+// columns): Wt[dp][f] (weights transposed, zero rows up to dp) and Cp[3][f] = mean | range |
+// RN(1/range), so the inner loop does 16-byte loads that are contiguous across the warp instead of
+// strided scalar loads and a division per column.
 __global__ void pad_weights_kernel(const float* __restrict__ W, int f, int d, int d0, int dc,
-                                   int dp, float* __restrict__ Wp) {
+                                   int dp, float* __restrict__ Wt, const float* __restrict__ mean,
+                                   const float* __restrict__ range, float* __restrict__ Cp) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= f * dp) return;
-  const int row = i / dp, j = i % dp;
-  Wp[i] = (j < dc) ? W[(size_t)row * d + d0 + j] : 0.f;
+  const int j = i / f, col = i % f;
+  Wt[i] = (j < dc) ? W[(size_t)col * d + d0 + j] : 0.f;
+  if (j == 0 && mean) {
+    const float rg = range[col];
+    Cp[col] = mean[col];
+    Cp[f + col] = rg;
+    Cp[2 * f + col] = 1.0f / rg;
+  }
+}
+
+// small, hot operands (weights, column parameters): cached loads
+template <int VEC>
+__device__ __forceinline__ void load_par_vec(const float* p, float (&v)[VEC]) {
+  if constexpr (VEC == 4) { float4 t = __ldg(reinterpret_cast<const float4*>(p)); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+  else if constexpr (VEC == 2) { float2 t = __ldg(reinterpret_cast<const float2*>(p)); v[0] = t.x; v[1] = t.y; }
+  else { v[0] = __ldg(p); }
 }
 
 template <int VEC>
@@ -32,11 +51,15 @@ __device__ __forceinline__ void load_row_vec(const float* p, float (&v)[VEC]) {
 // Rows per warp step (amortises the W loads): 4 for narrow outputs, 2 for wide (register budget).
 __host__ __device__ constexpr int proj_rows(int dp4) { return dp4 <= 2 ? 4 : 2; }
 
+// resident CTAs per SM the register budget is compiled for: narrow outputs need few registers, and
+// more resident warps mean more 16-byte loads in flight (the kernel is HBM-latency bound)
+__host__ __device__ constexpr int proj_min_ctas(int dp4) { return dp4 == 1 ? 3 : 2; }
+
 template <int VEC, int DP4, bool STD>
-__global__ void __launch_bounds__(kProjThreads, 2)
+__global__ void __launch_bounds__(kProjThreads, proj_min_ctas(DP4))
 project_kernel(const float* __restrict__ X, int64_t n, int f, int64_t ld,
-               const float* __restrict__ mean, const float* __restrict__ range,
-               const float* __restrict__ Wp, int d_total, int d0, int dc,
+               const float* __restrict__ Cp,
+               const float* __restrict__ Wt, int d_total, int d0, int dc,
                float* __restrict__ P, float* __restrict__ part_min, float* __restrict__ part_max) {
   constexpr int DP = DP4 * 4;
   constexpr int kProjRows = proj_rows(DP4);
@@ -65,22 +88,30 @@ project_kernel(const float* __restrict__ X, int64_t n, int f, int64_t ld,
         const int64_t row = min(row0 + r, n - 1);
         load_row_vec<VEC>(X + row * ld + col, x[r]);
       }
+      float z[kProjRows][VEC];
+      if constexpr (STD) {
+        float m[VEC], rg[VEC], ri[VEC];
+        load_par_vec<VEC>(Cp + col, m);
+        load_par_vec<VEC>(Cp + f + col, rg);
+        load_par_vec<VEC>(Cp + 2 * (size_t)f + col, ri);
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        float m = 0.f, rg = 1.f, ri = 1.f;
-        if constexpr (STD) { m = __ldg(mean + col + v); rg = __ldg(range + col + v); ri = 1.0f / rg; }
-        float w[DP];
+        for (int r = 0; r < kProjRows; ++r)
 #pragma unroll
-        for (int q = 0; q < DP4; ++q) {
-          const float4 t = __ldg(reinterpret_cast<const float4*>(Wp + (size_t)(col + v) * DP) + q);
-          w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
-        }
+          for (int v = 0; v < VEC; ++v) z[r][v] = standardize1(x[r][v], m[v], rg[v], ri[v]);
+      } else {
 #pragma unroll
-        for (int r = 0; r < kProjRows; ++r) {
-          const float z = STD ? standardize1(x[r][v], m, rg, ri) : x[r][v];
+        for (int r = 0; r < kProjRows; ++r)
 #pragma unroll
-          for (int j = 0; j < DP; ++j) acc[r][j] = fmaf(z, w[j], acc[r][j]);
-        }
+          for (int v = 0; v < VEC; ++v) z[r][v] = x[r][v];
+      }
+#pragma unroll
+      for (int j = 0; j < DP; ++j) {
+        float w[VEC];
+        load_par_vec<VEC>(Wt + (size_t)j * f + col, w);
+#pragma unroll
+        for (int r = 0; r < kProjRows; ++r)
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) acc[r][j] = fmaf(z[r][v], w[v], acc[r][j]);
       }
     }
     // warp all-reduce of the kProjRows x DP partial dot products
@@ -141,20 +172,21 @@ __global__ void project_minmax_kernel(const float* __restrict__ part_min, const 
   }
 }
 
-static int project_grid(int64_t n) {
-  const int64_t groups = ceil_div(n, 4);
-  return (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(groups, kProjWarps), (int64_t)kNumSMs * 8));
+// persistent grid: every resident CTA slot of the device, at most (upper bound used for workspace)
+static int project_grid(int64_t n, int ctas_per_sm = 4) {
+  const int64_t groups = ceil_div(n, 2);
+  return (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(groups, kProjWarps), (int64_t)kNumSMs * ctas_per_sm));
 }
 
 template <int VEC, bool STD>
 static void launch_project(int dp4, dim3 grid, cudaStream_t st, const float* X, int64_t n, int f,
-                           int64_t ld, const float* mean, const float* range, const float* Wp,
+                           int64_t ld, const float* Cp, const float* Wp,
                            int d, int d0, int dc, float* P, float* pmn, float* pmx) {
   switch (dp4) {
-    case 1: project_kernel<VEC, 1, STD><<<grid, kProjThreads, 0, st>>>(X, n, f, ld, mean, range, Wp, d, d0, dc, P, pmn, pmx); break;
-    case 2: project_kernel<VEC, 2, STD><<<grid, kProjThreads, 0, st>>>(X, n, f, ld, mean, range, Wp, d, d0, dc, P, pmn, pmx); break;
-    case 3: project_kernel<VEC, 3, STD><<<grid, kProjThreads, 0, st>>>(X, n, f, ld, mean, range, Wp, d, d0, dc, P, pmn, pmx); break;
-    default: project_kernel<VEC, 4, STD><<<grid, kProjThreads, 0, st>>>(X, n, f, ld, mean, range, Wp, d, d0, dc, P, pmn, pmx); break;
+    case 1: project_kernel<VEC, 1, STD><<<grid, kProjThreads, 0, st>>>(X, n, f, ld, Cp, Wp, d, d0, dc, P, pmn, pmx); break;
+    case 2: project_kernel<VEC, 2, STD><<<grid, kProjThreads, 0, st>>>(X, n, f, ld, Cp, Wp, d, d0, dc, P, pmn, pmx); break;
+    case 3: project_kernel<VEC, 3, STD><<<grid, kProjThreads, 0, st>>>(X, n, f, ld, Cp, Wp, d, d0, dc, P, pmn, pmx); break;
+    default: project_kernel<VEC, 4, STD><<<grid, kProjThreads, 0, st>>>(X, n, f, ld, Cp, Wp, d, d0, dc, P, pmn, pmx); break;
   }
 }
 
@@ -164,7 +196,7 @@ using namespace dcg;
 
 extern "C" size_t dcg_project_workspace_bytes(int64_t n, int f, int d) {
   if (n <= 0 || f <= 0 || d <= 0) return 0;
-  return align_up((size_t)f * 16 * sizeof(float), 256) +
+  return align_up((size_t)f * 16 * sizeof(float), 256) + align_up((size_t)f * 3 * sizeof(float), 256) +
          2 * align_up((size_t)project_grid(n) * d * sizeof(float), 256);
 }
 
@@ -180,19 +212,24 @@ extern "C" int dcg_project_f32(const float* X, int64_t n, int f, int64_t ld,
   char* w = (char*)ws;
   float* Wp = (float*)w;
   w += align_up((size_t)f * 16 * sizeof(float), 256);
-  const int grid = project_grid(n);
+  float4* Cp = (float4*)w;
+  w += align_up((size_t)f * 3 * sizeof(float), 256);
+  const int grid_max = project_grid(n);
   float* pmn = (float*)w;
-  w += align_up((size_t)grid * d * sizeof(float), 256);
+  w += align_up((size_t)grid_max * d * sizeof(float), 256);
   float* pmx = (float*)w;
+  int grid = grid_max;
   int vec = row_vec_width(X, ld);
   while (f % vec) vec >>= 1;
   const bool stdz = mean != nullptr;
   for (int d0 = 0; d0 < d; d0 += 16) {
     const int dc = min(16, d - d0);
     const int dp4 = (dc + 3) / 4, dp = dp4 * 4;
-    pad_weights_kernel<<<(unsigned)ceil_div((int64_t)f * dp, 256), 256, 0, st>>>(W, f, d, d0, dc, dp, Wp);
+    pad_weights_kernel<<<(unsigned)ceil_div((int64_t)f * dp, 256), 256, 0, st>>>(W, f, d, d0, dc, dp, Wp, mean, range, Cp);
     DCG_LAUNCH_CHECK();
-#define DCG_PROJ(V, S) launch_project<V, S>(dp4, dim3(grid), st, X, n, f, ld, mean, range, Wp, d, d0, dc, P, pmn, pmx)
+    // every chunk of 16 output columns uses the same grid (the min/max partials are indexed by CTA)
+    if (d0 == 0) grid = project_grid(n, proj_min_ctas(d > 16 ? 4 : dp4));
+#define DCG_PROJ(V, S) launch_project<V, S>(dp4, dim3(grid), st, X, n, f, ld, Cp, Wp, d, d0, dc, P, pmn, pmx)
     if (vec == 4) { if (stdz) DCG_PROJ(4, true); else DCG_PROJ(4, false); }
     else if (vec == 2) { if (stdz) DCG_PROJ(2, true); else DCG_PROJ(2, false); }
     else { if (stdz) DCG_PROJ(1, true); else DCG_PROJ(1, false); }

@@ -47,7 +47,7 @@ def test_argument_errors_without_gpu():
     assert lib.dcg_kmeans_step(p, 10, 40, 40, 4, p, 3, p, p, p, p, None, 1, p, 64, None) == -1001
     assert lib.dcg_kmeans_step(p, 10, 4, 4, 2, p, 3, p, p, p, p, None, 1, p, 64, None) == -1005
     assert lib.dcg_colstats_workspace_bytes(1000, 10) > 0
-    assert lib.dcg_cov_workspace_bytes(1000, 1000, 10, 0, 1) >= 148 * 2 * 128 * 128 * 8
+    assert lib.dcg_cov_workspace_bytes(1000, 1000, 10, 0, 1) >= 256 + 26 * 32     # 16 S_tau + 10 S0 super-tile descriptors
     assert lib.dcg_ticacov_out_doubles(3) == 2 + 3 + 18 + 6
 
 
@@ -130,6 +130,51 @@ def test_htica_block_diagonal_level1_equals_full():
         mask[s:e, s:e] = True
     T_blk = linalg.htica_level1(S0 * mask, St * mask, a, b, M, chunks, 3)
     np.testing.assert_allclose(T_full.numpy(), T_blk.numpy(), atol=1e-12)
+
+
+def _slow_mode_sums(F, n=6000, lag=5, slow=6, seed=0):
+    g = np.random.default_rng(seed)
+    rho = np.exp(-1.0 / (300.0 * 0.5 ** np.arange(slow)))
+    z = np.zeros((n, slow))
+    e = g.standard_normal((n, slow))
+    for t in range(1, n):
+        z[t] = rho * z[t - 1] + np.sqrt(1 - rho ** 2) * e[t]
+    X = z @ g.standard_normal((slow, F)) + 0.5 * g.standard_normal((n, F))
+    X = (X - X.mean(0)) / X.std(0)
+    M = n - lag
+    t = torch.from_numpy
+    return t(X[:M].T @ X[:M]), t(X[:M].T @ X[lag:]), t(X[:M].sum(0)), t(X[lag:].sum(0)), M
+
+
+@pytest.mark.parametrize("F,out", [(256, 3), (400, 5)])
+def test_partial_eigensolver_matches_dense_route(F, out, monkeypatch):
+    """The shift-and-invert iteration returns the eigenpairs of the dense Cholesky route
+    (mlcolvar cholesky_eigh) to 2e-8, far inside the 1e-5 parity tolerance."""
+    from deep_cartograph_b200 import linalg
+    S0, St, a, b, M = _slow_mode_sums(F)
+    monkeypatch.setattr(linalg, "_PARTIAL_MIN_F", 10 ** 9)
+    e_dense, V_dense = linalg.tica_from_sums(S0, St, a, b, M, out)
+    monkeypatch.setattr(linalg, "_PARTIAL_MIN_F", 192)
+    fast0 = linalg.EIG_STATS["fast"]
+    e_fast, V_fast = linalg.tica_from_sums(S0, St, a, b, M, out)
+    assert linalg.EIG_STATS["fast"] == fast0 + 1
+    np.testing.assert_allclose(e_fast.numpy(), e_dense.numpy(), rtol=1e-10)
+    np.testing.assert_allclose(V_fast.numpy(), V_dense.numpy(), atol=2e-8)
+
+
+def test_partial_eigensolver_falls_back_on_flat_spectrum():
+    """More eigenpairs requested than there are slow modes: the wanted eigenvalues sit in the
+    noise bulk, the iteration gives up and the dense route answers (same result as always)."""
+    from deep_cartograph_b200 import linalg
+    S0, St, a, b, M = _slow_mode_sums(256, slow=2)
+    dense0 = linalg.EIG_STATS["dense"]
+    evals, V = linalg.tica_from_sums(S0, St, a, b, M, 12)
+    assert linalg.EIG_STATS["dense"] == dense0 + 1
+    C0 = (S0 / M - torch.outer(a / M, a / M)).numpy()
+    Ct = (St / M - torch.outer(a / M, b / M)).numpy()
+    from oracle import cv_oracle
+    ref, _ = cv_oracle._cholesky_eigh(0.5 * (C0 + C0.T), 0.5 * (Ct + Ct.T), 1e-6, 12)
+    np.testing.assert_allclose(evals.numpy(), ref, rtol=1e-9, atol=1e-12)
 
 
 def test_tica_failure_raises_for_calculator_to_catch():
