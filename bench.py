@@ -261,8 +261,7 @@ def main():
             if shards is not None:
                 packed = shards.allreduce_sum_(torch.cat([sums.reshape(-1), counts]))
                 sums, counts = packed[:K * DIM].view(K, DIM), packed[K * DIM:]
-            nz = counts > 0
-            C = torch.where(nz[:, None], sums / counts.clamp(min=1.0)[:, None], C)
+            ops.kmeans_update_(C, sums.contiguous(), counts.contiguous())
       return evals, labels
 
     def sync_all():

@@ -18,13 +18,14 @@
 namespace dcg {
 
 constexpr int kKmThreads = 512;
-constexpr int kKmR = 2;                       // frames per thread
-constexpr int kKmTile = kKmThreads * kKmR;
+// frames per thread: more frames amortise the shared-memory centre loads and the loop overhead of
+// the screening pass; bounded by the 128-register budget of a 512-thread CTA
+__host__ __device__ constexpr int km_frames_per_thread(int dp) { return dp <= 12 ? 4 : 2; }
 constexpr size_t kKmSmemBudget = 200 * 1024;
 
 struct KmSmemPlan {
   size_t centers_off, csq_off, acc_off, total;
-  int smem_acc;
+  int smem_acc;   // number of privatised FP64 accumulator copies in shared memory (0 = global atomics)
 };
 
 static KmSmemPlan km_plan(int d, int dp, int k) {
@@ -33,9 +34,12 @@ static KmSmemPlan km_plan(int d, int dp, int k) {
   p.csq_off = (size_t)k * dp * sizeof(float);
   size_t o = align_up(p.csq_off + (size_t)k * sizeof(float), 16);
   p.acc_off = o;
+  // FP64 shared-memory atomics are CAS loops: with few clusters every thread of the CTA hits the
+  // same k*(d+1) words, so warps get private copies (warp w uses copy w % copies) while they fit
   const size_t acc_bytes = (size_t)k * (d + 1) * sizeof(double);
-  p.smem_acc = (o + acc_bytes <= kKmSmemBudget) ? 1 : 0;
-  p.total = o + (p.smem_acc ? acc_bytes : 0);
+  const size_t room = kKmSmemBudget > o ? kKmSmemBudget - o : 0;
+  p.smem_acc = (int)std::min<size_t>(room / acc_bytes, kKmThreads / 32);
+  p.total = o + (size_t)p.smem_acc * acc_bytes;
   return p;
 }
 
@@ -62,6 +66,8 @@ kmeans_step_kernel(const T* __restrict__ Y, int64_t n, int d, int64_t ld,
                    const double* __restrict__ centers, int k, int32_t* __restrict__ labels,
                    double* __restrict__ sums, double* __restrict__ counts, double* __restrict__ stats,
                    T* __restrict__ gap, int update_sums, KmSmemPlan plan) {
+  constexpr int kKmR = km_frames_per_thread(DP);
+  constexpr int kKmTile = kKmThreads * kKmR;
   extern __shared__ __align__(16) unsigned char smem[];
   float* c_s = reinterpret_cast<float*>(smem + plan.centers_off);
   float* csq_s = reinterpret_cast<float*>(smem + plan.csq_off);
@@ -82,7 +88,8 @@ kmeans_step_kernel(const T* __restrict__ Y, int64_t n, int d, int64_t ld,
     atomicMax(reinterpret_cast<int*>(&s_cmax2), __float_as_int((float)s));  // s >= 0: int order == float order
   }
   if (plan.smem_acc && update_sums)
-    for (int i = tid; i < k * (d + 1); i += kKmThreads) acc_s[i] = 0.0;
+    for (int i = tid; i < plan.smem_acc * k * (d + 1); i += kKmThreads) acc_s[i] = 0.0;
+  double* acc_w = acc_s + (size_t)((tid >> 5) % (plan.smem_acc > 0 ? plan.smem_acc : 1)) * k * (d + 1);
   __syncthreads();
   const float cmax2 = s_cmax2 * 1.0001f + 1e-30f;
   const float cmaxn = sqrtf(cmax2);
@@ -148,7 +155,7 @@ kmeans_step_kernel(const T* __restrict__ Y, int64_t n, int d, int64_t ld,
       if (labels[idx[r]] != l) { ++t_changed; labels[idx[r]] = l; }
       t_inertia += fmax(b + (double)xsq[r], 0.0);
       if (update_sums) {
-        double* a = plan.smem_acc ? (acc_s + (size_t)l * (d + 1)) : nullptr;
+        double* a = plan.smem_acc ? (acc_w + (size_t)l * (d + 1)) : nullptr;
         if (a) {
           for (int q = 0; q < d; ++q) atomicAdd(a + q, (double)yrow[q]);
           atomicAdd(a + d, 1.0);
@@ -172,13 +179,50 @@ kmeans_step_kernel(const T* __restrict__ Y, int64_t n, int d, int64_t ld,
   if (plan.smem_acc && update_sums) {
     __syncthreads();
     for (int i = tid; i < k * (d + 1); i += kKmThreads) {
-      const double v = acc_s[i];
+      double v = 0.0;
+      for (int c = 0; c < plan.smem_acc; ++c) v += acc_s[(size_t)c * k * (d + 1) + i];
       if (v != 0.0) {
         const int j = i / (d + 1), q = i - j * (d + 1);
         if (q < d) atomicAdd(sums + (size_t)j * d + q, v);
         else atomicAdd(counts + j, v);
       }
     }
+  }
+}
+
+// ---- M-step finish: centres = sums / counts (sklearn _average_centers: sums * (1 / count)) --------
+// One CTA.  info[0] = number of empty clusters.  When there is none, the centres are updated in
+// place and info[1] = sum ||c_new - c_old||^2 (the Lloyd driver's convergence test); with empty
+// clusters nothing is touched: the driver relocates them first (rare path).
+__global__ void kmeans_update_kernel(const double* __restrict__ sums, const double* __restrict__ counts,
+                                     int k, int d, double* __restrict__ centers, double* __restrict__ info) {
+  __shared__ int s_empty;
+  __shared__ double s_shift[32];
+  if (threadIdx.x == 0) s_empty = 0;
+  __syncthreads();
+  int empty = 0;
+  for (int j = threadIdx.x; j < k; j += blockDim.x) empty += counts[j] <= 0.0;
+  if (empty) atomicAdd(&s_empty, empty);
+  __syncthreads();
+  const int n_empty = s_empty;
+  double shift = 0.0;
+  if (n_empty == 0) {
+    for (int i = threadIdx.x; i < k * d; i += blockDim.x) {
+      const int j = i / d;
+      const double c_new = sums[i] * (1.0 / counts[j]);
+      const double df = c_new - centers[i];
+      shift = fma(df, df, shift);
+      centers[i] = c_new;
+    }
+  }
+  shift = warp_sum(shift);
+  if ((threadIdx.x & 31) == 0) s_shift[threadIdx.x >> 5] = shift;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_shift[w];
+    info[0] = (double)n_empty;
+    info[1] = t;
   }
 }
 
@@ -251,7 +295,7 @@ static int launch_kmeans(const T* Y, int64_t n, int d, int64_t ld, const double*
   int per_sm = 1;
   DCG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kKmThreads, plan.total));
   if (per_sm < 1) per_sm = 1;
-  const int64_t ntiles = ceil_div(n, kKmTile);
+  const int64_t ntiles = ceil_div(n, kKmThreads * km_frames_per_thread(DP));
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, (int64_t)kNumSMs * per_sm));
   kern<<<grid, kKmThreads, plan.total, st>>>(Y, n, d, ld, centers, k, labels, sums, counts, stats,
                                              gap, update_sums, plan);
@@ -299,6 +343,15 @@ extern "C" int dcg_kmeans_step(const void* Y, int64_t n, int d, int64_t ld, int 
                                   (float*)gap, update_sums, st);
   return dispatch_kmeans<double>((const double*)Y, n, d, ld, centers, k, labels, sums, counts, stats,
                                  (double*)gap, update_sums, st);
+}
+
+extern "C" int dcg_kmeans_update(const double* sums, const double* counts, int k, int d,
+                                 double* centers, double* info, void* stream) {
+  if (!sums || !counts || !centers || !info) return DCG_E_NULL;
+  if (k < 1 || d < 1 || d > 32) return DCG_E_SHAPE;
+  kmeans_update_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(sums, counts, k, d, centers, info);
+  DCG_LAUNCH_CHECK();
+  return 0;
 }
 
 extern "C" size_t dcg_nearest_workspace_bytes(int64_t n, int d, int k) {

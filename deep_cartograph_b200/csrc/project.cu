@@ -49,7 +49,7 @@ __device__ __forceinline__ void load_row_vec(const float* p, float (&v)[VEC]) {
 
 // DP4 = padded output width / 4 (1..4).  STD: apply (x-mean)/range.
 // Rows per warp step (amortises the W loads): 4 for narrow outputs, 2 for wide (register budget).
-__host__ __device__ constexpr int proj_rows(int dp4) { return dp4 <= 2 ? 4 : 2; }
+__host__ __device__ constexpr int proj_rows(int dp4) { return dp4 <= 3 ? 4 : 2; }
 
 // resident CTAs per SM the register budget is compiled for: narrow outputs need few registers, and
 // more resident warps mean more 16-byte loads in flight (the kernel is HBM-latency bound)
@@ -212,7 +212,7 @@ extern "C" int dcg_project_f32(const float* X, int64_t n, int f, int64_t ld,
   char* w = (char*)ws;
   float* Wp = (float*)w;
   w += align_up((size_t)f * 16 * sizeof(float), 256);
-  float4* Cp = (float4*)w;
+  float* Cp = (float*)w;
   w += align_up((size_t)f * 3 * sizeof(float), 256);
   const int grid_max = project_grid(n);
   float* pmn = (float*)w;

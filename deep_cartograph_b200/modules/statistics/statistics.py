@@ -114,15 +114,18 @@ def kmeans_lloyd(Y: torch.Tensor, init_centers: torch.Tensor, max_iter: int = 30
             sums = packed[:k * d].view(k, d)
             counts = packed[k * d:k * d + k]
             stats = packed[k * d + k:]
-        empty = torch.nonzero(counts == 0).flatten()
-        if empty.numel() > 0:
+        # M-step finish on the device (centres updated in place unless a cluster is empty);
+        # ONE host read per iteration: [n_empty, shift, changed]
+        info = ops.kmeans_update_(C, sums.contiguous(), counts.contiguous())
+        n_empty, shift_tot, changed = torch.cat([info, stats[:1]]).tolist()
+        if n_empty > 0:
+            empty = torch.nonzero(counts == 0).flatten()
             sums, counts = _relocate_empty(Yc, C, labels, sums, counts, empty, shards)
-        C_new = C.clone()
-        nz = counts > 0
-        C_new[nz] = sums[nz] * (1.0 / counts[nz]).unsqueeze(1)
-        shift_tot = float(((C_new - C) ** 2).sum().item())
-        changed = float(stats[0].item())
-        C = C_new
+            C_new = C.clone()
+            nz = counts > 0
+            C_new[nz] = sums[nz] * (1.0 / counts[nz]).unsqueeze(1)
+            shift_tot = float(((C_new - C) ** 2).sum().item())
+            C = C_new
         n_iter = it + 1
         if changed == 0:
             strict = True

@@ -244,6 +244,25 @@ def kmeans_step(Y: torch.Tensor, centers: torch.Tensor, labels: torch.Tensor,
     return {"sums": sums, "counts": counts, "stats": stats, "gap": gap}
 
 
+def kmeans_update_(centers: torch.Tensor, sums: torch.Tensor, counts: torch.Tensor,
+                   info: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """M-step finish on the device: ``info[0]`` = number of empty clusters; when there is none
+    ``centers`` (k x d FP64) becomes ``sums * (1 / counts)`` IN PLACE and ``info[1]`` = total squared
+    centre shift.  Returns ``info`` (2 x FP64, device); nothing is synchronised."""
+    _need_cuda("centers", centers, torch.float64)
+    _need_cuda("sums", sums, torch.float64)
+    _need_cuda("counts", counts, torch.float64)
+    if not (centers.is_contiguous() and sums.is_contiguous() and counts.is_contiguous()):
+        raise ValueError("centers, sums and counts must be contiguous")
+    k, d = centers.shape
+    if info is None:
+        info = torch.empty(2, dtype=torch.float64, device=centers.device)
+    _lib.call("dcg_kmeans_update", sums.data_ptr(), counts.data_ptr(), k, d, centers.data_ptr(),
+              info.data_ptr(), _stream())
+    _count(1)
+    return info
+
+
 def nearest_to_centers(Y: torch.Tensor, centers: torch.Tensor) -> torch.Tensor:
     """Index of the first arg-min sample per centre (reference statistics.py:370-377)."""
     _need_cuda("Y", Y)

@@ -110,6 +110,16 @@ int dcg_kmeans_step(const void* Y, int64_t n, int d, int64_t ld, int dtype_bytes
                     double* sums, double* counts, double* stats, void* gap,
                     int update_sums, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- K1: M-step finish ------------------------------------------------------------------------
+ * Replaces sklearn `_average_centers` + the centre-shift test of `_kmeans_single_lloyd`
+ * (sklearn/cluster/_k_means_common.pyx, _kmeans.py:703-740) as reached from
+ * statistics.kmeans_clustering (statistics.py:159-197).  info[0] = number of empty clusters
+ * (counts == 0).  If there is none: centers[j] = sums[j] * (1 / counts[j]) in place and
+ * info[1] = sum_j ||c_new - c_old||^2; otherwise centers are left untouched (the caller relocates
+ * the empty clusters first, sklearn/cluster/_k_means_common.pyx:167-211).  All FP64.            */
+int dcg_kmeans_update(const double* sums, const double* counts, int k, int d,
+                      double* centers, double* info, void* stream);
+
 /* ---- K3: nearest sample to each centre -------------------------------------------------------
  * Replaces `statistics.find_centroids` (statistics.py:370-377): argmin_t ||y_t - c_j||_2 per
  * centre j, first index on ties, evaluated in FP64.  argmin is int64[k].                        */

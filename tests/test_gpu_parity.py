@@ -253,6 +253,48 @@ def test_kmeans_large_k_against_oracle(dev):
         np.testing.assert_allclose(res["counts"].cpu().numpy(), np.bincount(ref_lab, minlength=k))
 
 
+@pytest.mark.gpu
+def test_kmeans_update_matches_sklearn_average_centers(dev):
+    """dcg_kmeans_update: centres = sums * (1 / counts) in place + squared shift; untouched when a
+    cluster is empty (the driver relocates first)."""
+    from deep_cartograph_b200 import ops
+    rng = np.random.default_rng(3)
+    for k, d in [(5, 2), (1000, 10), (37, 32)]:
+        sums = rng.standard_normal((k, d)); counts = rng.integers(1, 50, size=k).astype(np.float64)
+        C = rng.standard_normal((k, d))
+        Cd = _cuda(C, dev)
+        info = ops.kmeans_update_(Cd, _cuda(sums, dev), _cuda(counts, dev)).cpu().numpy()
+        ref = sums * (1.0 / counts)[:, None]
+        assert info[0] == 0
+        assert np.array_equal(Cd.cpu().numpy(), ref)
+        np.testing.assert_allclose(info[1], ((ref - C) ** 2).sum(), rtol=1e-12)
+        counts[k // 2] = 0.0
+        Cd = _cuda(C, dev)
+        info = ops.kmeans_update_(Cd, _cuda(sums, dev), _cuda(counts, dev)).cpu().numpy()
+        assert info[0] == 1 and np.array_equal(Cd.cpu().numpy(), C)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k,d", [(3, 2), (16, 10), (100, 4), (64, 7)])
+def test_kmeans_small_k_sums_with_private_accumulators(dev, k, d):
+    """Few clusters: every warp accumulates into its own shared-memory copy; the merged FP64 sums
+    and counts must equal the float64 scatter-add."""
+    from deep_cartograph_b200 import ops
+    rng = np.random.default_rng(k * 100 + d)
+    n = 200003
+    cent = rng.uniform(-1, 1, size=(k, d))
+    Y = (cent[rng.integers(0, k, size=n)] + 0.05 * rng.standard_normal((n, d))).astype(np.float32)
+    lab = torch.full((n,), -1, dtype=torch.int32, device=dev)
+    res = ops.kmeans_step(_cuda(Y, dev), _cuda(cent, dev), lab)
+    ref_lab, best, second = oracle.kmeans_assign(Y.astype(np.float64), cent)
+    got = lab.cpu().numpy()
+    diff = np.flatnonzero(got != ref_lab)
+    assert np.all(second[diff] - best[diff] <= 1e-12), len(diff)
+    sums = np.zeros((k, d)); np.add.at(sums, got, Y.astype(np.float64))
+    np.testing.assert_allclose(res["sums"].cpu().numpy(), sums, rtol=1e-11, atol=1e-9)
+    np.testing.assert_array_equal(res["counts"].cpu().numpy(), np.bincount(got, minlength=k))
+
+
 def test_kmeans_empty_cluster_relocation(dev):
     from deep_cartograph_b200.modules.statistics import statistics
     X = np.array([[0.0, 0.0], [0.1, 0.0], [5.0, 5.0], [5.1, 5.0], [9.0, 9.0]])

@@ -295,7 +295,18 @@ def test_lloyd_driver_control_flow_with_emulated_kernel(monkeypatch, kmeans_ref)
         return {"sums": torch.from_numpy(sums), "counts": torch.from_numpy(np.bincount(lab, minlength=k).astype(np.float64)),
                 "stats": stats, "gap": None}
 
+    def fake_update(C, sums, counts, info=None):
+        # dcg_kmeans_update: centres in place unless a cluster is empty; info = [n_empty, shift]
+        n_empty = int((counts == 0).sum())
+        shift = 0.0
+        if n_empty == 0:
+            C_new = sums * (1.0 / counts).unsqueeze(1)
+            shift = float(((C_new - C) ** 2).sum())
+            C.copy_(C_new)
+        return torch.tensor([float(n_empty), shift], dtype=torch.float64)
+
     monkeypatch.setattr(ops, "kmeans_step", fake_step)
+    monkeypatch.setattr(ops, "kmeans_update_", fake_update)
     for name in ("blobs_d2_k5", "blobs_d4_k10_grid", "uniform_d3_k7_grid"):
         X = torch.from_numpy(kmeans_ref[f"{name}_X"])
         res = statistics.kmeans_lloyd(X, torch.from_numpy(kmeans_ref[f"{name}_init"]))
