@@ -33,6 +33,14 @@ __device__ __forceinline__ void load_vec(const float* p, float (&v)[VEC]) {
   }
 }
 
+// VEC floats of one row; the last vector of a row may be partial (f not a multiple of VEC)
+template <int VEC>
+__device__ __forceinline__ void load_vec_tail(const float* p, int valid, float (&v)[VEC]) {
+  if (valid >= VEC) { load_vec<VEC>(p, v); return; }
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) v[i] = i < valid ? ldg_stream1(p + i) : 0.f;
+}
+
 template <int VEC>
 __global__ void __launch_bounds__(kStatThreads)
 colstats_partial_kernel(const float* __restrict__ X, int64_t n, int f, int64_t ld, int64_t rows_per_cta,
@@ -42,7 +50,8 @@ colstats_partial_kernel(const float* __restrict__ X, int64_t n, int f, int64_t l
   const int col0 = (blockIdx.x * 32 + lane) * VEC;            // first column of this thread
   const int64_t row_begin = (int64_t)blockIdx.y * rows_per_cta;
   const int64_t row_end = min(n, row_begin + rows_per_cta);
-  const bool active = col0 < f;                                // f % VEC == 0 guaranteed by host
+  const bool active = col0 < f;
+  const int valid = f - col0;                                  // columns of this thread's vector inside the matrix
 
   // Shifted sums: d = x - K with K = the tile's first row of this column, so every FP32 quantity
   // is of the size of the column's spread (not its mean).  FP32 partials are promoted to FP64
@@ -55,13 +64,13 @@ colstats_partial_kernel(const float* __restrict__ X, int64_t n, int f, int64_t l
 
   if (active) {
     const float* base = X + col0;
-    load_vec<VEC>(base + row_begin * ld, shift);
+    load_vec_tail<VEC>(base + row_begin * ld, valid, shift);
     int64_t r = row_begin + warp;
     // unrolled: kStatUnroll independent loads in flight per thread
     for (; r + (int64_t)(kStatUnroll - 1) * kStatWarps < row_end; r += (int64_t)kStatUnroll * kStatWarps) {
       float x[kStatUnroll][VEC];
 #pragma unroll
-      for (int u = 0; u < kStatUnroll; ++u) load_vec<VEC>(base + (r + (int64_t)u * kStatWarps) * ld, x[u]);
+      for (int u = 0; u < kStatUnroll; ++u) load_vec_tail<VEC>(base + (r + (int64_t)u * kStatWarps) * ld, valid, x[u]);
       float s[VEC], q[VEC];
 #pragma unroll
       for (int v = 0; v < VEC; ++v) { s[v] = 0.f; q[v] = 0.f; }
@@ -82,7 +91,7 @@ colstats_partial_kernel(const float* __restrict__ X, int64_t n, int f, int64_t l
     }
     for (; r < row_end; r += kStatWarps) {
       float x[VEC];
-      load_vec<VEC>(base + r * ld, x);
+      load_vec_tail<VEC>(base + r * ld, valid, x);
       cnt += 1;
 #pragma unroll
       for (int v = 0; v < VEC; ++v) {
@@ -210,8 +219,7 @@ extern "C" int dcg_colstats_f32(const float* X, int64_t n, int f, int64_t ld,
   float* pmin = (float*)w;
   w += align_up((size_t)rb * f * sizeof(float), 256);
   float* pmax = (float*)w;
-  int vec = row_vec_width(X, ld);
-  while (f % vec) vec >>= 1;
+  const int vec = row_vec_width(X, ld);      // f need not be a multiple: the last vector of a row is guarded
   dim3 grid((unsigned)ceil_div(f, 32 * vec), (unsigned)rb);
   if (vec == 4)
     colstats_partial_kernel<4><<<grid, kStatThreads, 0, st>>>(X, n, f, ld, rpc, part, pmin, pmax);

@@ -17,18 +17,20 @@ constexpr int kProjThreads = kProjWarps * 32;
 // columns): Wt[dp][f] (weights transposed, zero rows up to dp) and Cp[3][f] = mean | range |
 // RN(1/range), so the inner loop does 16-byte loads that are contiguous across the warp instead of
 // strided scalar loads and a division per column.
-__global__ void pad_weights_kernel(const float* __restrict__ W, int f, int d, int d0, int dc,
+// Rows of both arrays are fp = f rounded up to 4 floats long; the padding columns hold weight 0
+// (and mean 0, range 1), so a partial last vector of an X row contributes nothing.
+__global__ void pad_weights_kernel(const float* __restrict__ W, int f, int fp, int d, int d0, int dc,
                                    int dp, float* __restrict__ Wt, const float* __restrict__ mean,
                                    const float* __restrict__ range, float* __restrict__ Cp) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= f * dp) return;
-  const int j = i / f, col = i % f;
-  Wt[i] = (j < dc) ? W[(size_t)col * d + d0 + j] : 0.f;
+  if (i >= fp * dp) return;
+  const int j = i / fp, col = i % fp;
+  Wt[i] = (j < dc && col < f) ? W[(size_t)col * d + d0 + j] : 0.f;
   if (j == 0 && mean) {
-    const float rg = range[col];
-    Cp[col] = mean[col];
-    Cp[f + col] = rg;
-    Cp[2 * f + col] = 1.0f / rg;
+    const float rg = col < f ? range[col] : 1.f;
+    Cp[col] = col < f ? mean[col] : 0.f;
+    Cp[fp + col] = rg;
+    Cp[2 * fp + col] = 1.0f / rg;
   }
 }
 
@@ -38,6 +40,17 @@ __device__ __forceinline__ void load_par_vec(const float* p, float (&v)[VEC]) {
   if constexpr (VEC == 4) { float4 t = __ldg(reinterpret_cast<const float4*>(p)); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
   else if constexpr (VEC == 2) { float2 t = __ldg(reinterpret_cast<const float2*>(p)); v[0] = t.x; v[1] = t.y; }
   else { v[0] = __ldg(p); }
+}
+
+template <int VEC>
+__device__ __forceinline__ void load_row_vec(const float* p, float (&v)[VEC]);
+
+// the last vector of a row may be partial (f not a multiple of VEC): missing columns read as 0
+template <int VEC>
+__device__ __forceinline__ void load_row_tail(const float* p, int valid, float (&v)[VEC]) {
+  if (valid >= VEC) { load_row_vec<VEC>(p, v); return; }
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) v[i] = i < valid ? ldg_stream1(p + i) : 0.f;
 }
 
 template <int VEC>
@@ -57,7 +70,7 @@ __host__ __device__ constexpr int proj_min_ctas(int dp4) { return dp4 == 1 ? 3 :
 
 template <int VEC, int DP4, bool STD>
 __global__ void __launch_bounds__(kProjThreads, proj_min_ctas(DP4))
-project_kernel(const float* __restrict__ X, int64_t n, int f, int64_t ld,
+project_kernel(const float* __restrict__ X, int64_t n, int f, int fp, int64_t ld,
                const float* __restrict__ Cp,
                const float* __restrict__ Wt, int d_total, int d0, int dc,
                float* __restrict__ P, float* __restrict__ part_min, float* __restrict__ part_max) {
@@ -86,14 +99,14 @@ project_kernel(const float* __restrict__ X, int64_t n, int f, int64_t ld,
       for (int r = 0; r < kProjRows; ++r) {
         // rows past the end re-read the last valid row (results discarded)
         const int64_t row = min(row0 + r, n - 1);
-        load_row_vec<VEC>(X + row * ld + col, x[r]);
+        load_row_tail<VEC>(X + row * ld + col, f - col, x[r]);
       }
       float z[kProjRows][VEC];
       if constexpr (STD) {
         float m[VEC], rg[VEC], ri[VEC];
         load_par_vec<VEC>(Cp + col, m);
-        load_par_vec<VEC>(Cp + f + col, rg);
-        load_par_vec<VEC>(Cp + 2 * (size_t)f + col, ri);
+        load_par_vec<VEC>(Cp + fp + col, rg);
+        load_par_vec<VEC>(Cp + 2 * (size_t)fp + col, ri);
 #pragma unroll
         for (int r = 0; r < kProjRows; ++r)
 #pragma unroll
@@ -107,7 +120,7 @@ project_kernel(const float* __restrict__ X, int64_t n, int f, int64_t ld,
 #pragma unroll
       for (int j = 0; j < DP; ++j) {
         float w[VEC];
-        load_par_vec<VEC>(Wt + (size_t)j * f + col, w);
+        load_par_vec<VEC>(Wt + (size_t)j * fp + col, w);
 #pragma unroll
         for (int r = 0; r < kProjRows; ++r)
 #pragma unroll
@@ -179,14 +192,14 @@ static int project_grid(int64_t n, int ctas_per_sm = 4) {
 }
 
 template <int VEC, bool STD>
-static void launch_project(int dp4, dim3 grid, cudaStream_t st, const float* X, int64_t n, int f,
+static void launch_project(int dp4, dim3 grid, cudaStream_t st, const float* X, int64_t n, int f, int fp,
                            int64_t ld, const float* Cp, const float* Wp,
                            int d, int d0, int dc, float* P, float* pmn, float* pmx) {
   switch (dp4) {
-    case 1: project_kernel<VEC, 1, STD><<<grid, kProjThreads, 0, st>>>(X, n, f, ld, Cp, Wp, d, d0, dc, P, pmn, pmx); break;
-    case 2: project_kernel<VEC, 2, STD><<<grid, kProjThreads, 0, st>>>(X, n, f, ld, Cp, Wp, d, d0, dc, P, pmn, pmx); break;
-    case 3: project_kernel<VEC, 3, STD><<<grid, kProjThreads, 0, st>>>(X, n, f, ld, Cp, Wp, d, d0, dc, P, pmn, pmx); break;
-    default: project_kernel<VEC, 4, STD><<<grid, kProjThreads, 0, st>>>(X, n, f, ld, Cp, Wp, d, d0, dc, P, pmn, pmx); break;
+    case 1: project_kernel<VEC, 1, STD><<<grid, kProjThreads, 0, st>>>(X, n, f, fp, ld, Cp, Wp, d, d0, dc, P, pmn, pmx); break;
+    case 2: project_kernel<VEC, 2, STD><<<grid, kProjThreads, 0, st>>>(X, n, f, fp, ld, Cp, Wp, d, d0, dc, P, pmn, pmx); break;
+    case 3: project_kernel<VEC, 3, STD><<<grid, kProjThreads, 0, st>>>(X, n, f, fp, ld, Cp, Wp, d, d0, dc, P, pmn, pmx); break;
+    default: project_kernel<VEC, 4, STD><<<grid, kProjThreads, 0, st>>>(X, n, f, fp, ld, Cp, Wp, d, d0, dc, P, pmn, pmx); break;
   }
 }
 
@@ -196,7 +209,7 @@ using namespace dcg;
 
 extern "C" size_t dcg_project_workspace_bytes(int64_t n, int f, int d) {
   if (n <= 0 || f <= 0 || d <= 0) return 0;
-  return align_up((size_t)f * 16 * sizeof(float), 256) + align_up((size_t)f * 3 * sizeof(float), 256) +
+  return align_up((size_t)(f + 3) * 16 * sizeof(float), 256) + align_up((size_t)(f + 3) * 3 * sizeof(float), 256) +
          2 * align_up((size_t)project_grid(n) * d * sizeof(float), 256);
 }
 
@@ -211,25 +224,25 @@ extern "C" int dcg_project_f32(const float* X, int64_t n, int f, int64_t ld,
   cudaStream_t st = (cudaStream_t)stream;
   char* w = (char*)ws;
   float* Wp = (float*)w;
-  w += align_up((size_t)f * 16 * sizeof(float), 256);
+  w += align_up((size_t)(f + 3) * 16 * sizeof(float), 256);
   float* Cp = (float*)w;
-  w += align_up((size_t)f * 3 * sizeof(float), 256);
+  w += align_up((size_t)(f + 3) * 3 * sizeof(float), 256);
+  const int fp = (f + 3) / 4 * 4;
   const int grid_max = project_grid(n);
   float* pmn = (float*)w;
   w += align_up((size_t)grid_max * d * sizeof(float), 256);
   float* pmx = (float*)w;
   int grid = grid_max;
-  int vec = row_vec_width(X, ld);
-  while (f % vec) vec >>= 1;
+  const int vec = row_vec_width(X, ld);     // f need not be a multiple: the last vector of a row is guarded
   const bool stdz = mean != nullptr;
   for (int d0 = 0; d0 < d; d0 += 16) {
     const int dc = min(16, d - d0);
     const int dp4 = (dc + 3) / 4, dp = dp4 * 4;
-    pad_weights_kernel<<<(unsigned)ceil_div((int64_t)f * dp, 256), 256, 0, st>>>(W, f, d, d0, dc, dp, Wp, mean, range, Cp);
+    pad_weights_kernel<<<(unsigned)ceil_div((int64_t)fp * dp, 256), 256, 0, st>>>(W, f, fp, d, d0, dc, dp, Wp, mean, range, Cp);
     DCG_LAUNCH_CHECK();
     // every chunk of 16 output columns uses the same grid (the min/max partials are indexed by CTA)
     if (d0 == 0) grid = project_grid(n, proj_min_ctas(d > 16 ? 4 : dp4));
-#define DCG_PROJ(V, S) launch_project<V, S>(dp4, dim3(grid), st, X, n, f, ld, Cp, Wp, d, d0, dc, P, pmn, pmx)
+#define DCG_PROJ(V, S) launch_project<V, S>(dp4, dim3(grid), st, X, n, f, fp, ld, Cp, Wp, d, d0, dc, P, pmn, pmx)
     if (vec == 4) { if (stdz) DCG_PROJ(4, true); else DCG_PROJ(4, false); }
     else if (vec == 2) { if (stdz) DCG_PROJ(2, true); else DCG_PROJ(2, false); }
     else { if (stdz) DCG_PROJ(1, true); else DCG_PROJ(1, false); }

@@ -35,7 +35,8 @@ _PARTIAL_MIN_F = 192
 def _shift_invert_topk(B: torch.Tensor, Ct: torch.Tensor, out: int, tol: float = 1e-12,
                        max_rounds: int = 10):
     """The `out` largest eigenpairs of Ct v = lambda B v (B SPD) by shift-and-invert subspace
-    iteration with Rayleigh-Ritz, FP64.
+    iteration with Rayleigh-Ritz, FP64.  ``B`` / ``Ct`` are (F, F) or a batch (nb, F, F) of
+    independent pencils (hTICA level 1: all blocks in one set of launches).
 
     K = sigma B - Ct is SPD for sigma > lambda_max (TICA eigenvalues are autocorrelations, <= 1 up
     to estimator noise).  X <- K^-1 B X converges to the eigenvalues closest to sigma at the rate
@@ -45,78 +46,91 @@ def _shift_invert_topk(B: torch.Tensor, Ct: torch.Tensor, out: int, tol: float =
     bound: 0.9 ms per application at F = 1000, against 20 us per skinny GEMM), so a solve is a
     handful of F x F x b GEMMs instead of the dense route's tridiagonalisation (12 ms at F = 1000).
     Ritz pairs are accepted only when ||Ct x - theta B x|| <= tol ||Ct||_F ||x|| for all `out` of
-    them; returns None otherwise (flat spectrum, shift not found) and the caller goes dense."""
-    F = B.shape[0]
+    them (in every pencil of the batch); returns None otherwise (flat spectrum, shift not found)
+    and the caller goes dense."""
+    batched = B.dim() == 3
+    if not batched:
+        B, Ct = B.unsqueeze(0), Ct.unsqueeze(0)
+    nb, F = B.shape[0], B.shape[-1]
     b = min(F, out + 8)
-    nrm = torch.linalg.matrix_norm(Ct)                       # Frobenius norm, residual scale
+    nrm = torch.linalg.matrix_norm(Ct).unsqueeze(-1)         # (nb, 1) Frobenius norms, residual scale
     eye = torch.eye(F, dtype=B.dtype, device=B.device)
+    eye_b = torch.eye(b, dtype=B.dtype, device=B.device)
 
     def factor(sig):
+        """sig: (nb, 1, 1).  Returns (K, Lk^-1) or None if any K is not positive definite."""
         Kmat = sig * B - Ct
         Lk, info = torch.linalg.cholesky_ex(Kmat)
-        if int(info.item()) != 0:
+        if int(info.abs().max().item()) != 0:
             return None
-        return Kmat, torch.linalg.solve_triangular(Lk, eye, upper=False)      # K, Lk^-1
+        return Kmat, torch.linalg.solve_triangular(Lk, eye.expand(nb, F, F), upper=False)
 
-    sigma, fac = 1.05, None
+    sigma = torch.full((nb, 1, 1), 1.05, dtype=B.dtype, device=B.device)
+    fac = None
     for _ in range(3):
         fac = factor(sigma)
         if fac is not None:
             break
-        sigma *= 2.0
+        sigma = sigma * 2.0
     if fac is None:
         return None
 
     def solve(Z):
         Kmat, Li = fac
-        Y = Li.T @ (Li @ Z)
-        return Y + Li.T @ (Li @ (Z - Kmat @ Y))             # one step of iterative refinement
+        Y = Li.mT @ (Li @ Z)
+        return Y + Li.mT @ (Li @ (Z - Kmat @ Y))            # one step of iterative refinement
 
-    X = _start_block(F, b, B.device)
+    X = _start_block(F, b, B.device).expand(nb, F, b)
     it = 0
     reshifted = False
     for _ in range(max_rounds):
         for _ in range(4):
             X = solve(B @ X)
-            X = X / torch.linalg.norm(X, dim=0, keepdim=True)
+            X = X / torch.linalg.norm(X, dim=-2, keepdim=True)
             it += 1
         # Rayleigh-Ritz in span(X):  (X^T Ct X) s = theta (X^T B X) s
         BX = B @ X
         CX = Ct @ X
-        Gb = X.T @ BX
-        Lb, info = torch.linalg.cholesky_ex(0.5 * (Gb + Gb.T))
-        if int(info.item()) != 0:
+        Gb = X.mT @ BX
+        Lb, info = torch.linalg.cholesky_ex(0.5 * (Gb + Gb.mT))
+        if int(info.abs().max().item()) != 0:
             return None
-        Lbi = torch.linalg.solve_triangular(Lb, torch.eye(b, dtype=B.dtype, device=B.device), upper=False)
-        Hs = Lbi @ (X.T @ CX) @ Lbi.T
-        theta, S = torch.linalg.eigh(0.5 * (Hs + Hs.T))
-        theta = theta.flip(0)
-        S = Lbi.T @ S.flip(1)
+        Lbi = torch.linalg.solve_triangular(Lb, eye_b.expand(nb, b, b), upper=False)
+        Hs = Lbi @ (X.mT @ CX) @ Lbi.mT
+        theta, S = torch.linalg.eigh(0.5 * (Hs + Hs.mT))
+        theta = theta.flip(-1)
+        S = Lbi.mT @ S.flip(-1)
         X = X @ S
-        res = torch.linalg.norm(CX @ S[:, :out] - (BX @ S[:, :out]) * theta[:out], dim=0)
-        worst = float((res / (nrm * torch.linalg.norm(X[:, :out], dim=0))).max().item())
+        res = torch.linalg.norm(CX @ S[..., :out] - (BX @ S[..., :out]) * theta[:, None, :out], dim=-2)
+        rel = res / (nrm * torch.linalg.norm(X[..., :out], dim=-2))
+        # one host read per round: worst residual + the Ritz values the shift logic needs
+        host = torch.cat([rel.max().reshape(1), theta[:, 0], theta[:, out - 1], theta[:, b - 1],
+                          sigma.reshape(-1)]).tolist()
+        worst = host[0]
         if worst <= tol:
-            EIG_STATS["fast"] += 1
+            EIG_STATS["fast"] += nb
             EIG_STATS["last_iters"] = it
-            return theta[:out], X[:, :out]
+            ev, V = theta[:, :out], X[..., :out]
+            return (ev, V) if batched else (ev[0], V[0])
         if not reshifted:
             reshifted = True
-            # predicted rate with the current shift; if it is slow, move the shift close to the top
-            # Ritz value (which approaches lambda_max from below) and refactorise once
-            th = theta.tolist()
-            rate = (sigma - th[out - 1]) / max(sigma - th[b - 1], 1e-300)
-            if rate > 0.25:
-                spread = max(th[0] - th[b - 1], 1e-12)
+            th0, tho, thb, sig = (host[1 + i * nb:1 + (i + 1) * nb] for i in range(4))
+
+            def worst_rate(sg):
+                return max((sg[i] - tho[i]) / max(sg[i] - thb[i], 1e-300) for i in range(nb))
+            # predicted rate with the current shift; if it is slow, move every shift close to its
+            # top Ritz value (which approaches lambda_max from below) and refactorise once
+            if worst_rate(sig) > 0.25:
                 for mult in (0.05, 0.2, 0.8):
-                    s2 = th[0] + mult * spread + 1e-9 * max(1.0, abs(th[0]))
-                    if s2 >= sigma:
-                        break
-                    f2 = factor(s2)
+                    s2 = [min(sig[i], th0[i] + mult * max(th0[i] - thb[i], 1e-12) + 1e-9 * max(1.0, abs(th0[i])))
+                          for i in range(nb)]
+                    f2 = factor(torch.tensor(s2, dtype=B.dtype, device=B.device).reshape(nb, 1, 1))
                     if f2 is not None:
-                        fac, sigma = f2, s2
+                        fac, sig = f2, s2
+                        sigma = torch.tensor(s2, dtype=B.dtype, device=B.device).reshape(nb, 1, 1)
                         break
-                rate = (sigma - th[out - 1]) / max(sigma - th[b - 1], 1e-300)
             # flat spectrum below the wanted eigenvalues: more steps than the dense route costs
+            rate = worst_rate(sig)
             if rate >= 1.0 or math.log(tol) / math.log(max(rate, 1e-300)) > 4 * max_rounds:
                 return None
     return None
@@ -125,41 +139,43 @@ def _shift_invert_topk(B: torch.Tensor, Ct: torch.Tensor, out: int, tol: float =
 def _cholesky_eigh(C0: torch.Tensor, Ct: torch.Tensor, reg: float, out: int):
     """B = C0 + reg I; L = chol(B); A = L^-1 Ct L^-T; eigh; descending; V = L^-T U;
     unit-L2 columns; sign(row 0) >= 0; first ``out`` (mlcolvar cholesky_eigh + TICA).
+    Inputs are (F, F) or a batch (nb, F, F).
 
     Only the leading ``out`` eigenpairs are needed, so for F >= 192 they come from the
     shift-and-invert iteration above (same generalised eigenvectors: L^-T u solves
     Ct v = lambda B v); the dense route is the fallback and the small-F path."""
-    F = C0.shape[0]
+    F = C0.shape[-1]
     B = C0 + reg * torch.eye(F, dtype=C0.dtype, device=C0.device)
     L, info = torch.linalg.cholesky_ex(B)
-    if int(info.item()) != 0:
+    if int(info.abs().max().item()) != 0:
         raise RuntimeError("TICA: C0 + reg*I is not positive definite")
     out = min(out, F)
     got = None
     if F >= _PARTIAL_MIN_F and 2 * (out + 8) < F:
         got = _shift_invert_topk(B, Ct, out)
     if got is None:
-        EIG_STATS["dense"] += 1
+        EIG_STATS["dense"] += 1 if C0.dim() == 2 else C0.shape[0]
         Y = torch.linalg.solve_triangular(L, Ct, upper=False)             # L^-1 Ct
-        A = torch.linalg.solve_triangular(L, Y.T, upper=False).T          # (L^-1 (L^-1 Ct)^T)^T
-        evals, U = torch.linalg.eigh(0.5 * (A + A.T))
-        V = torch.linalg.solve_triangular(L.T, U.flip(1)[:, :out], upper=True)    # L^-T U
-        got = evals.flip(0)[:out], V
+        A = torch.linalg.solve_triangular(L, Y.mT, upper=False).mT        # (L^-1 (L^-1 Ct)^T)^T
+        evals, U = torch.linalg.eigh(0.5 * (A + A.mT))
+        V = torch.linalg.solve_triangular(L.mT, U.flip(-1)[..., :out], upper=True)    # L^-T U
+        got = evals.flip(-1)[..., :out], V
     evals, V = got
-    V = V / torch.linalg.norm(V, dim=0, keepdim=True)
-    V = V * torch.sign(V[0:1, :])
+    V = V / torch.linalg.norm(V, dim=-2, keepdim=True)
+    V = V * torch.sign(V[..., 0:1, :])
     return evals, V
 
 
 def tica_from_sums(S0, St, a, b, M: int, out: int, reg: float = 1e-6):
     """TICA eigenpairs from raw sums.  ``S0`` must be fully symmetric.  mu = a/M is subtracted
-    from BOTH series, covariances are divided by M, C_tau is symmetrised."""
+    from BOTH series, covariances are divided by M, C_tau is symmetrised.  Inputs may carry a
+    leading batch dimension (independent problems of equal size)."""
     mu = a / M
     nu = b / M
-    C0 = S0 / M - torch.outer(mu, mu)
-    C0 = 0.5 * (C0 + C0.T)
-    Ct = St / M - torch.outer(mu, nu)
-    Ct = 0.5 * (Ct + Ct.T)
+    C0 = S0 / M - mu.unsqueeze(-1) * mu.unsqueeze(-2)
+    C0 = 0.5 * (C0 + C0.mT)
+    Ct = St / M - mu.unsqueeze(-1) * nu.unsqueeze(-2)
+    Ct = 0.5 * (Ct + Ct.mT)
     return _cholesky_eigh(C0, Ct, reg, out)
 
 
@@ -186,12 +202,24 @@ def htica_chunks(F: int, num_subspaces: int) -> List[Tuple[int, int]]:
 
 
 def htica_level1(S0, St, a, b, M: int, chunks, sub_dim: int, reg: float = 1e-6) -> torch.Tensor:
-    """Per-block TICA (level 1); returns the block-diagonal transform T1 (F x S1)."""
+    """Per-block TICA (level 1); returns the block-diagonal transform T1 (F x S1).  Blocks of equal
+    width (all but possibly the last, cv_calculator.py:2331-2334) are solved as ONE batch."""
     F = S0.shape[0]
-    blocks = []
-    for (s, e) in chunks:
-        _, Vb = tica_from_sums(S0[s:e, s:e], St[s:e, s:e], a[s:e], b[s:e], M, sub_dim, reg)
-        blocks.append(Vb)
+    blocks = [None] * len(chunks)
+    by_width = {}
+    for i, (s, e) in enumerate(chunks):
+        by_width.setdefault(e - s, []).append(i)
+    for width, idxs in by_width.items():
+        if len(idxs) == 1:
+            s, e = chunks[idxs[0]]
+            blocks[idxs[0]] = tica_from_sums(S0[s:e, s:e], St[s:e, s:e], a[s:e], b[s:e], M, sub_dim, reg)[1]
+            continue
+        sl = [chunks[i] for i in idxs]
+        _, Vb = tica_from_sums(torch.stack([S0[s:e, s:e] for s, e in sl]), torch.stack([St[s:e, s:e] for s, e in sl]),
+                               torch.stack([a[s:e] for s, e in sl]), torch.stack([b[s:e] for s, e in sl]),
+                               M, sub_dim, reg)
+        for j, i in enumerate(idxs):
+            blocks[i] = Vb[j]
     S1 = sum(v.shape[1] for v in blocks)
     T1 = torch.zeros((F, S1), dtype=S0.dtype, device=S0.device)
     c = 0

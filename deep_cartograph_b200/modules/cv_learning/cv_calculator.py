@@ -170,13 +170,20 @@ class CVCalculator:
         if X.dtype != torch.float32:
             X = X.to(torch.float32)
         lag = int(self.configuration.get("lag_time") or 0)
-        if shards is not None and lag > 0:
-            # spare rows after the shard so the lag halo is received in place (no second copy)
-            buf = torch.empty((X.shape[0] + lag, X.shape[1]), dtype=torch.float32, device=dev)
-            buf[:X.shape[0]].copy_(X, non_blocking=True)
-            self.training_data = buf[:X.shape[0]]
+        n_in, f_in = X.shape
+        halo = lag if (shards is not None and lag > 0) else 0
+        ld = (f_in + 3) // 4 * 4
+        aligned = (X.device == dev and X.dim() == 2 and X.stride(1) == 1 and X.stride(0) % 4 == 0
+                   and X.data_ptr() % 16 == 0)
+        if halo or not aligned:
+            # HBM layout: rows padded to a multiple of 4 floats so every row starts 16-byte aligned
+            # (16-byte loads in every kernel; e.g. 4950 features -> row stride 4952), plus spare rows
+            # after the shard so the lag halo is received in place (no second copy)
+            buf = torch.empty((n_in + halo, ld), dtype=torch.float32, device=dev)
+            buf[:n_in, :f_in].copy_(X, non_blocking=True)
+            self.training_data = buf[:n_in, :f_in]
         else:
-            self.training_data = X.to(dev, non_blocking=True).contiguous()
+            self.training_data = X                       # already resident with 16-byte aligned rows
         self.shards = shards
         self.training_data_labels = traj_labels
         n, f = self.training_data.shape
@@ -487,10 +494,17 @@ class HTICACalculator(LinearCalculator):
     def _htica_level2(self, T1: torch.Tensor, lag: int) -> torch.Tensor:
         mean, rng = self._norm_on_device()
         T1f = T1.to(torch.float32)
+        # T1 is block diagonal: block b projects only its own columns of X, so the level-1
+        # projections are ONE pass over X in total (each call reads one column block)
+        chunks = linalg.htica_chunks(self.num_features, self.num_subspaces)
         parts = []
-        for c0 in range(0, T1f.shape[1], 64):              # projection kernel: d <= 64 per call
-            Pc, _, _ = ops.project(self.training_data, T1f[:, c0:c0 + 64].contiguous(), mean, rng, minmax=False)
+        c = 0
+        for (s0, e0) in chunks:
+            w = min(self.subspaces_dimension, e0 - s0)
+            Pc, _, _ = ops.project(self.training_data[:, s0:e0], T1f[s0:e0, c:c + w].contiguous(),
+                                   mean[s0:e0], rng[s0:e0], minmax=False)
             parts.append(Pc)
+            c += w
         P = parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)
         if self.shards is not None:
             P = self.shards.with_halo(P, lag)

@@ -65,25 +65,32 @@ class FrameShards:
         n, f = X.shape
         if n < lag:
             raise ValueError(f"shard of {n} frames is shorter than the lag {lag}")
+        # in place when X is the leading view of a 2-D buffer (possibly with padded rows) that has
+        # `lag` spare rows after the shard
         base = X._base if X._base is not None else None
-        room = (base is not None and base.dim() == 2 and base.shape[1] == f and base.is_contiguous()
-                and base.data_ptr() == X.data_ptr() and base.shape[0] >= n + lag)
+        room = (base is not None and base.dim() == 2 and base.shape[1] >= f and base.stride(1) == 1
+                and base.stride(0) == X.stride(0) and base.data_ptr() == X.data_ptr()
+                and base.shape[0] >= n + lag)
         has_next = self.rank + 1 < self.world
         if has_next:
-            out = base[:n + lag] if room else torch.cat([X, torch.empty((lag, f), dtype=X.dtype, device=X.device)])
+            out = base[:n + lag, :f] if room else torch.cat([X, torch.empty((lag, f), dtype=X.dtype, device=X.device)])
             halo = out[n:n + lag]
         else:
             out = X
             halo = None
         head = X[:lag].contiguous()
+        recv = None
         ops = []
         if self.rank > 0:
             ops.append(dist.P2POp(dist.isend, head, self._global(self.rank - 1), group=self.group))
         if has_next:
-            ops.append(dist.P2POp(dist.irecv, halo, self._global(self.rank + 1), group=self.group))
+            recv = halo if halo.is_contiguous() else torch.empty((lag, f), dtype=X.dtype, device=X.device)
+            ops.append(dist.P2POp(dist.irecv, recv, self._global(self.rank + 1), group=self.group))
         if ops:
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
+        if recv is not None and recv is not halo:
+            halo.copy_(recv)
         return out
 
     def _global(self, group_rank: int) -> int:

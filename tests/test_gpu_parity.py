@@ -166,6 +166,68 @@ def test_cov_linearity_over_frame_chunks(dev, engine):
         assert err < 2e-6, (k, err)
 
 
+@pytest.mark.parametrize("f,ld_pad,block", [(990, 0, 0), (990, 2, 0), (495, 1, 0), (998, 0, 499), (4950 // 5, 0, 99)])
+def test_cov_unaligned_rows_and_block_origins(dev, f, ld_pad, block):
+    """Row strides that are not multiples of 4 floats (8- and 4-byte load paths of the tcgen05
+    engine), feature counts that are not multiples of 4, and diagonal blocks that start at odd
+    columns (the C3 shape: blocks of 495 features)."""
+    from deep_cartograph_b200 import ops
+    n, lag = 3000, 7
+    X = synth_features(n, f, seed=f + ld_pad)
+    buf = torch.zeros((n, f + ld_pad), dtype=torch.float32, device=dev)
+    buf[:, :f] = torch.from_numpy(X).to(dev)
+    Xd = buf[:, :f]                                           # row stride f + ld_pad floats
+    st = oracle.column_stats(X)
+    m, r = oracle.prepare_normalization(st, "mean_std")
+    Z = oracle.standardize(X, m, r)
+    s = ops.lagged_covariance(Xd, lag, _cuda(m.astype(np.float32), dev), _cuda(r.astype(np.float32), dev),
+                              block=block, engine="tc_3xtf32")
+    _assert_cov_close(s, oracle.lagged_sums(Z, lag), 1e-5, block=block)
+
+
+def test_cov_full_size_c2_properties(dev):
+    """BASELINE config C2 (1M frames x 1000 features, lag 10) through size-independent properties:
+    (i) linearity -- the sums over the whole series equal the sums over two shards with a lag halo
+    (what the multi-GPU path relies on); (ii) the diagonal of S0 equals the column sums of squares
+    and the column sums equal a float64 reduction; (iii) S_tau at lag 0 shifted rows: trace identity
+    tr(St) = sum_t z_t . z_{t+lag} evaluated in float64 on the device."""
+    from deep_cartograph_b200 import ops
+    from deep_cartograph_b200.synthetic import feature_matrix
+    n, f, lag = 1_000_000, 1000, 10
+    X = feature_matrix(n, f, 0, n, dev)
+    stt = ops.column_stats(X)
+    mean = stt["mean"].float()
+    rng = torch.sqrt(stt["m2"] / (n - 1)).float()
+    whole = ops.lagged_covariance(X, lag, mean, rng, engine="tc_3xtf32")
+    h = 437_123                                               # deliberately not a multiple of anything
+    first = ops.lagged_covariance(X[:h + lag], lag, mean, rng, engine="tc_3xtf32")
+    second = ops.lagged_covariance(X[h:], lag, mean, rng, engine="tc_3xtf32")
+    assert first["M"] + second["M"] == whole["M"] == n - lag
+    scale = whole["S0"].abs().max().item()
+    for key in ("S0", "St"):
+        tot = first[key] + second[key]
+        ref = whole[key]
+        if key == "S0":
+            tot, ref = torch.triu(tot), torch.triu(ref)
+        assert (tot - ref).abs().max().item() / scale < 3e-6, key
+    for key in ("a", "b"):
+        assert (first[key] + second[key] - whole[key]).abs().max().item() < 1e-3
+    # float64 column reductions on the device (chunked to bound memory)
+    M = n - lag
+    sq = torch.zeros(f, dtype=torch.float64, device=dev)
+    sm = torch.zeros(f, dtype=torch.float64, device=dev)
+    tr = torch.zeros((), dtype=torch.float64, device=dev)
+    for s0 in range(0, M, 100_000):
+        e0 = min(M, s0 + 100_000)
+        Z = ((X[s0:e0 + lag] - mean) / rng).double()
+        zt, zl = Z[:e0 - s0], Z[lag:lag + e0 - s0]
+        sq += (zt * zt).sum(0); sm += zt.sum(0); tr += (zt * zl).sum()
+    d0 = torch.diagonal(whole["S0"])
+    assert ((d0 - sq).abs() / sq).max().item() < 1e-5
+    assert (whole["a"] - sm).abs().max().item() < 2e-3
+    assert abs(torch.diagonal(whole["St"]).sum().item() - tr.item()) / abs(tr.item()) < 1e-5
+
+
 # ------------------------------------------------------------------------------------------------
 # A9/A10 projection
 # ------------------------------------------------------------------------------------------------

@@ -162,6 +162,24 @@ def test_partial_eigensolver_matches_dense_route(F, out, monkeypatch):
     np.testing.assert_allclose(V_fast.numpy(), V_dense.numpy(), atol=2e-8)
 
 
+def test_partial_eigensolver_batched_blocks_match_single_solves():
+    """hTICA level 1 solves its equal-width blocks as one batch; every block must equal its own
+    single solve."""
+    from deep_cartograph_b200 import linalg
+    S0, St, a, b, M = _slow_mode_sums(512, n=5000, slow=6, seed=4)
+    chunks = linalg.htica_chunks(512, 2)
+    assert chunks == [(0, 256), (256, 512)]
+    fast0 = linalg.EIG_STATS["fast"]
+    T1 = linalg.htica_level1(S0, St, a, b, M, chunks, 3)
+    assert linalg.EIG_STATS["fast"] == fast0 + 2
+    c = 0
+    for (s0, e0) in chunks:
+        _, Vb = linalg.tica_from_sums(S0[s0:e0, s0:e0], St[s0:e0, s0:e0], a[s0:e0], b[s0:e0], M, 3)
+        np.testing.assert_allclose(T1[s0:e0, c:c + 3].numpy(), Vb.numpy(), atol=2e-8)
+        assert float(T1[:s0, c:c + 3].abs().max()) == 0.0 if s0 else True
+        c += 3
+
+
 def test_partial_eigensolver_falls_back_on_flat_spectrum():
     """More eigenpairs requested than there are slow modes: the wanted eigenvalues sit in the
     noise bulk, the iteration gives up and the dense route answers (same result as always)."""
