@@ -148,6 +148,9 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host thread (set before
+    # numpy / torch / sklearn are imported)
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     steps, warmup = max(1, args.steps), max(0, min(args.warmup, 1))
     cb, mean_s = time_reference(CPU_SAMPLE_FRAMES, args.features, steps, warmup)
     line = {"impl": "reference", "metric": "frames/s, TICA C0/Ctau + projection + KMeans (hot path)",
@@ -300,8 +303,12 @@ def main():
     cov_s = float(cov_ms.item()) * 1e-3
     achieved = alg_flops / cov_s / 1e12
     issued_mult = {"tc_3xtf32": 3.0, "tc_1xtf32": 1.0, "simt_f32": 1.0}[engine]
+    # DRAM bytes per launch of this kernel at this shape, from the committed ncu --set full capture
+    # (profiles/r1_cov_tc_v2_ncu_summary.txt: dram__bytes_read.sum + dram__bytes_write.sum)
+    traffic = 9.95e9 if (engine == "tc_3xtf32" and n == N_PER_GPU and f == F) else None
     roofline = {"bound": "tensor", "kernel": f"cov_lag ({engine})", "achieved": achieved, "peak": tf32_peak,
-                "unit": "TFLOP/s", "frac": achieved / tf32_peak, "traffic": None,
+                "unit": "TFLOP/s", "frac": achieved / tf32_peak, "traffic": traffic,
+                "traffic_note": "bytes/launch (ncu); algorithmic bytes/launch = 4*F*n = %.3g" % (4.0 * f * n),
                 "issued_tflops": achieved * issued_mult, "frac_issued": achieved * issued_mult / tf32_peak,
                 "kernel_ms": cov_s * 1e3, "share_of_step": cov_s * 1e3 / ms_per_step,
                 "peak_source": f"{peaks['source']} bf16 burst / 2 (TF32 : bf16 = 1 : 2 on tcgen05)",

@@ -252,6 +252,32 @@ def test_projection_matches_float64(dev, n, f, d):
     np.testing.assert_allclose(P2.cpu().numpy(), ref, atol=1e-4 * max(1.0, np.abs(ref).max()))
 
 
+@pytest.mark.parametrize("n,f,d,ld", [(5003, 990, 10, 992), (3001, 495, 5, 496), (2050, 1000, 12, 1000),
+                                      (1027, 126, 3, 128), (4097, 4950 // 5, 16, 992), (999, 390, 7, 400)])
+def test_projection_padded_rows(dev, n, f, d, ld):
+    """16-byte aligned rows (the layout load_training_tensor produces: row stride rounded up to 4
+    floats, NaN in the padding) take the 16-byte load path with a guarded last vector, including
+    feature counts that are not multiples of 4 and row counts that are not multiples of the row group."""
+    from deep_cartograph_b200 import ops
+    X = synth_features(n, f, seed=d + f)
+    buf = torch.full((n, ld), float("nan"), dtype=torch.float32, device=dev)
+    buf[:, :f] = torch.from_numpy(X).to(dev)
+    st = oracle.column_stats(X)
+    m, r = oracle.prepare_normalization(st, "mean_std")
+    W = (np.random.default_rng(d).standard_normal((f, d)) / np.sqrt(f)).astype(np.float32)
+    ref = oracle.project(oracle.standardize(X, m, r), W)
+    P, pmin, pmax = ops.project(buf[:, :f], _cuda(W, dev), _cuda(m.astype(np.float32), dev),
+                                _cuda(r.astype(np.float32), dev))
+    got = P.cpu().numpy()
+    assert np.isfinite(got).all()
+    np.testing.assert_allclose(got, ref, atol=1e-4 * max(1.0, np.abs(ref).max()))
+    assert np.array_equal(pmin.cpu().numpy(), got.min(axis=0))
+    assert np.array_equal(pmax.cpu().numpy(), got.max(axis=0))
+    stt = ops.column_stats(buf[:, :f])                        # same layout through the statistics kernel
+    np.testing.assert_allclose(stt["mean"].cpu().numpy(), st["mean"], rtol=2e-7)
+    np.testing.assert_array_equal(stt["min"].cpu().numpy(), st["min"])
+
+
 # ------------------------------------------------------------------------------------------------
 # K1 KMeans
 # ------------------------------------------------------------------------------------------------

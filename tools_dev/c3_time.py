@@ -53,5 +53,30 @@ for rep in range(2):
     print(f"rep {rep}: n={n} f={f} (ld {ld}): stats {ms[0]:.1f} ms | hTICA sums+eig {ms[1]:.1f} ms | projection {ms[2]:.1f} ms | "
           f"KMeans k={k} x {res['n_iter']} iters {ms[3]:.1f} ms | total {tot:.1f} ms = {n / tot / 1e3:.2f} Mframes/s; "
           f"eig stats {linalg.EIG_STATS}; launches {ops.KERNEL_LAUNCHES - launches0}", flush=True)
+# finer breakdown of compute_cv (block-diagonal level 1, eigen stage, level 2)
+chunks = linalg.htica_chunks(f, 10)
+for rep in range(2):
+    t = [ev()]
+    s1 = calc._lagged_sums(lag, block=f // 10)
+    t.append(ev())
+    T1 = linalg.htica_level1(s1["S0"], s1["St"], s1["a"], s1["b"], s1["M"], chunks, 5)
+    t.append(ev())
+    mean, rng = calc._norm_on_device()
+    T1f = T1.to(torch.float32)
+    parts = []
+    c = 0
+    for (s0, e0) in chunks:
+        Pc, _, _ = ops.project(calc.training_data[:, s0:e0], T1f[s0:e0, c:c + 5].contiguous(), mean[s0:e0], rng[s0:e0], minmax=False)
+        parts.append(Pc); c += 5
+    P = torch.cat(parts, dim=1)
+    t.append(ev())
+    s2 = ops.lagged_covariance(P, lag)
+    t.append(ev())
+    _, V2 = linalg.tica_from_sums(ops.symmetrize_upper(s2["S0"]), s2["St"], s2["a"], s2["b"], s2["M"], d)
+    t.append(ev())
+    torch.cuda.synchronize()
+    ms = [t[i].elapsed_time(t[i + 1]) for i in range(len(t) - 1)]
+    print(f"compute_cv breakdown rep {rep}: level-1 sums {ms[0]:.1f} | level-1 eig (10 x 495, batched) {ms[1]:.1f} | "
+          f"level-1 projection {ms[2]:.1f} | level-2 sums (50 feat.) {ms[3]:.1f} | level-2 eig {ms[4]:.1f} ms", flush=True)
 W = torch.as_tensor(calc.cv)
 print("cv weights", tuple(W.shape), "finite", bool(torch.isfinite(W).all()))
