@@ -179,6 +179,32 @@ def tica_from_sums(S0, St, a, b, M: int, out: int, reg: float = 1e-6):
     return _cholesky_eigh(C0, Ct, reg, out)
 
 
+def restandardize_sums(s: dict, m0: torch.Tensor, r0: torch.Tensor, mean: torch.Tensor,
+                       rng: torch.Tensor) -> dict:
+    """Raw sums of z' = (x - m0) / r0  ->  raw sums of z = (x - mean) / rng, exactly (FP64):
+    z = alpha z' + beta per feature with alpha = r0 / rng, beta = (m0 - mean) / rng, so
+        S0 = A S0' A + (A a') beta^T + beta (A a')^T + M beta beta^T
+        St = A St' A + (A a') beta^T + beta (A b')^T + M beta beta^T
+        a  = A a' + M beta,   b = A b' + M beta                      (A = diag(alpha)).
+    Used when the sums were accumulated under provisional standardisation parameters while the
+    matrix was still arriving on the device.  ``S0`` must be fully symmetric."""
+    al = r0.to(torch.float64) / rng.to(torch.float64)
+    be = (m0.to(torch.float64) - mean.to(torch.float64)) / rng.to(torch.float64)
+    M = float(s["M"])
+    Aa = al * s["a"]
+    Ab = al * s["b"]
+    out = dict(s)
+    bb = M * torch.outer(be, be)
+    if s.get("S0") is not None:
+        x = torch.outer(Aa, be)
+        out["S0"] = al[:, None] * s["S0"] * al[None, :] + x + x.T + bb
+    if s.get("St") is not None:
+        out["St"] = al[:, None] * s["St"] * al[None, :] + torch.outer(Aa, be) + torch.outer(be, Ab) + bb
+    out["a"] = Aa + M * be
+    out["b"] = Ab + M * be
+    return out
+
+
 def pca_from_sums(S_all, s_all, N: int, d: int):
     """sklearn covariance-eigh PCA + the reference's sign rule (cv_calculator.py:2204-2215)."""
     mu = s_all / N

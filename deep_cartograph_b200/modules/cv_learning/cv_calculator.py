@@ -175,23 +175,29 @@ class CVCalculator:
         ld = (f_in + 3) // 4 * 4
         aligned = (X.device == dev and X.dim() == 2 and X.stride(1) == 1 and X.stride(0) % 4 == 0
                    and X.data_ptr() % 16 == 0)
+        self.shards = shards
+        self._spec = None
+        st = None
         if halo or not aligned:
             # HBM layout: rows padded to a multiple of 4 floats so every row starts 16-byte aligned
             # (16-byte loads in every kernel; e.g. 4950 features -> row stride 4952), plus spare rows
             # after the shard so the lag halo is received in place (no second copy)
             buf = torch.empty((n_in + halo, ld), dtype=torch.float32, device=dev)
-            buf[:n_in, :f_in].copy_(X, non_blocking=True)
             self.training_data = buf[:n_in, :f_in]
+            if X.device.type == "cpu" and self.backend.get("overlap_h2d", True):
+                st = self._stream_in(X)
+            else:
+                self.training_data.copy_(X, non_blocking=True)
         else:
             self.training_data = X                       # already resident with 16-byte aligned rows
-        self.shards = shards
         self.training_data_labels = traj_labels
         n, f = self.training_data.shape
         self.features_ref_labels = list(features_labels) if features_labels is not None else [f"f{i}" for i in range(f)]
         self.num_features = f
         logger.info(f"Number of features: {self.num_features}")
 
-        st = ops.column_stats(self.training_data)
+        if st is None:
+            st = ops.column_stats(self.training_data)
         if shards is not None:
             st = shards.merge_stats(st)
         self.num_frames = int(st["n"])
@@ -206,6 +212,94 @@ class CVCalculator:
         }
         self.features_norm_mean, self.features_norm_range = self.prepare_normalization()
         self._dev_norm = None
+
+    # ---- host -> device streaming with speculative sums ------------------------------------------
+    def _sums_plan(self):
+        """(lag, block, want_st) of the covariance sums ``compute_cv`` will ask for, or None."""
+        return None
+
+    def _provisional_norm(self, st: dict):
+        """Device-side (mean, range) of the configured mode from the statistics of the rows seen so
+        far (float32, |range| < 1e-8 -> 1).  Only used to condition the speculative sums."""
+        n = st["n"]
+        mean = st["mean"].to(torch.float32)
+        if self.feats_norm_mode is None:
+            return torch.zeros_like(mean), torch.ones_like(mean)
+        if self.feats_norm_mode == "mean_std":
+            m, r = mean, torch.sqrt(st["m2"] / max(n - 1, 1)).to(torch.float32)
+        elif self.feats_norm_mode == "min_max_range1":
+            m, r = st["min"], st["max"] - st["min"]
+        elif self.feats_norm_mode == "min_max_range2":
+            m, r = (st["min"] + st["max"]) / 2, (st["max"] - st["min"]) / 2
+        else:
+            raise ValueError(f"Normalization mode {self.feats_norm_mode} not recognized.")
+        return m.contiguous(), torch.where(r.abs() < 1e-8, torch.ones_like(r), r).contiguous()
+
+    def _stream_in(self, X: torch.Tensor) -> dict:
+        """Copy the host matrix to the device in row chunks on a copy stream; as each chunk lands the
+        compute stream takes its column statistics and -- when the calculator knows which sums it
+        will need -- accumulates the lagged covariance sums of the rows seen so far under
+        PROVISIONAL standardisation parameters (from a strided row sample).  The exact sums follow
+        from the provisional ones by an FP64 affine correction once the global statistics are known
+        (``linalg.restandardize_sums``), so the contraction overlaps the PCIe transfer instead of
+        following it.  Returns the merged column statistics of this shard."""
+        data = self.training_data
+        n, f = data.shape
+        dev = data.device
+        plan = self._sums_plan() if self.backend.get("speculative_sums", True) else None
+        chunk_bytes = int(self.backend.get("h2d_chunk_bytes", 256 << 20))
+        rows = max(1, min(n, chunk_bytes // max(1, 4 * f)))
+        if plan is not None:
+            rows = max(rows, 4 * plan[0] + 1)
+        bounds = [(c0, min(n, c0 + rows)) for c0 in range(0, n, rows)]
+        if len(bounds) > 1 and bounds[-1][1] - bounds[-1][0] <= (plan[0] if plan else 0):
+            bounds[-2] = (bounds[-2][0], n)                   # no chunk shorter than the lag
+            bounds.pop()
+        main = torch.cuda.current_stream(dev)
+        copier = torch.cuda.Stream(dev)
+        copier.wait_stream(main)                              # the buffer was allocated on `main`
+        events = []
+        with torch.cuda.stream(copier):
+            for c0, c1 in bounds:
+                data[c0:c1].copy_(X[c0:c1], non_blocking=True)
+                e = torch.cuda.Event()
+                e.record(copier)
+                events.append(e)
+        parts, acc, norm0, start = [], None, None, 0
+        engine = self.backend.get("cov_engine")
+        if plan is not None:
+            # provisional parameters: statistics of ~2048 evenly spaced rows, taken on the host before
+            # any byte has moved (spans the whole series, so slow drifts do not bias it the way the
+            # first chunk's statistics would)
+            idx = torch.linspace(0, n - 1, steps=min(n, 2048)).round().to(torch.int64)
+            smp = X.index_select(0, idx).to(torch.float64)
+            m = smp.shape[0]
+            mu = smp.mean(dim=0)
+            norm0 = self._provisional_norm({
+                "n": m, "mean": mu.to(dev), "m2": ((smp - mu) ** 2).sum(dim=0).to(dev),
+                "min": smp.min(dim=0).values.to(torch.float32).to(dev),
+                "max": smp.max(dim=0).values.to(torch.float32).to(dev)})
+        for (c0, c1), e in zip(bounds, events):
+            main.wait_event(e)
+            parts.append(ops.column_stats(data[c0:c1]))
+            if plan is None:
+                continue
+            lag, block, want_st = plan
+            if c1 - start <= lag:
+                continue
+            s = ops.lagged_covariance(data[start:c1], lag, norm0[0], norm0[1], block=block,
+                                      engine=engine, want_st=want_st)
+            if acc is None:
+                acc = s
+            else:
+                for k in ("S0", "St", "a", "b"):
+                    if s.get(k) is not None:
+                        acc[k] += s[k]
+                acc["M"] += s["M"]
+            start = c1 - lag                                  # the last `lag` rows pair with the next chunk
+        if plan is not None and acc is not None:
+            self._spec = {"plan": plan, "norm0": norm0, "sums": acc, "rows_done": start + plan[0]}
+        return ops.merge_column_stats(parts)
 
     def prepare_normalization(self) -> Tuple[np.ndarray, np.ndarray]:
         """(mean, range) per normalisation mode; |range| < 1e-8 -> 1 (reference :308-363)."""
@@ -410,11 +504,47 @@ class LinearCalculator(CVCalculator):
         if self.shards is not None:
             X = self.shards.with_halo(X, lag)
         engine = self.backend.get("cov_engine")
-        s = ops.lagged_covariance(X, lag, mean, rng, block=block, engine=engine, want_st=want_st)
+        s = self._take_speculative_sums(X, lag, block, want_st, mean, rng, engine)
+        if s is None:
+            s = ops.lagged_covariance(X, lag, mean, rng, block=block, engine=engine, want_st=want_st)
         if self.shards is not None:
             s = self.shards.allreduce_sums(s)
-        s["S0"] = ops.symmetrize_upper(s["S0"])
+        if not s.get("_S0_full"):
+            s["S0"] = ops.symmetrize_upper(s["S0"])
+        s.pop("_S0_full", None)
         return s
+
+    def _take_speculative_sums(self, X, lag, block, want_st, mean, rng, engine):
+        """Exact sums of this rank's rows from the ones accumulated during the host->device copy,
+        or None (no speculation, other parameters, or provisional statistics too far from the final
+        ones: the split-precision contraction is accurate relative to sum z'^2 = M (1 + delta^2), so
+        a provisional centre more than one standard deviation off, or a scale off by more than 2x,
+        would cost accuracy -- then the sums are recomputed on the resident matrix)."""
+        spec, self._spec = getattr(self, "_spec", None), None
+        if spec is None or spec["plan"] != (lag, block, want_st):
+            return None
+        m0, r0 = spec["norm0"]
+        be = ((m0.double() - mean.double()) / rng.double()).abs().max()
+        al = r0.double() / rng.double()
+        worst = torch.stack([be, al.max(), 1.0 / al.min()]).tolist()
+        if not (worst[0] <= 1.0 and worst[1] <= 2.0 and worst[2] <= 2.0):
+            logger.debug("Speculative sums discarded (provisional statistics off by %.2f sigma)" % worst[0])
+            return None
+        s = spec["sums"]
+        done = spec["rows_done"]                               # pairs t < done - lag are in `s`
+        if X.shape[0] > done:                                  # lag halo of the next shard arrived since
+            t = ops.lagged_covariance(X[done - lag:], lag, m0, r0, block=block, engine=engine, want_st=want_st)
+            for k in ("S0", "St", "a", "b"):
+                if t.get(k) is not None:
+                    s[k] += t[k]
+            s["M"] += t["M"]
+        s["S0"] = ops.symmetrize_upper(s["S0"])
+        if block:
+            # outside the diagonal blocks the kernel leaves zeros and the consumers never look
+            pass
+        out = linalg.restandardize_sums(s, m0, r0, mean, rng)
+        out["_S0_full"] = True
+        return out
 
 
 class PCACalculator(LinearCalculator):
@@ -424,6 +554,9 @@ class PCACalculator(LinearCalculator):
     def __init__(self, configuration: Optional[Dict] = None, output_path: Optional[str] = None):
         super().__init__(configuration, output_path)
         self.cv_name = "pca"
+
+    def _sums_plan(self):
+        return (0, 0, False)
 
     def compute_cv(self):
         if self.training_data is None:
@@ -441,6 +574,10 @@ class TICACalculator(LinearCalculator):
     def __init__(self, configuration: Optional[Dict] = None, output_path: Optional[str] = None):
         super().__init__(configuration, output_path)
         self.cv_name = "tica"
+
+    def _sums_plan(self):
+        lag = self.configuration.get("lag_time")
+        return (int(lag), 0, True) if lag else None
 
     def compute_cv(self):
         lag = self.configuration.get("lag_time")
@@ -462,6 +599,16 @@ class HTICACalculator(LinearCalculator):
         self.cv_name = "htica"
         self.num_subspaces = self.configuration.get("num_subspaces")
         self.subspaces_dimension = self.configuration.get("subspaces_dimension")
+
+    def _sums_plan(self):
+        lag = self.configuration.get("lag_time")
+        if not lag or self.training_data is None or not self.num_subspaces:
+            return None
+        F = self.training_data.shape[1]
+        if F // self.num_subspaces == 0:
+            return None
+        full = F <= int(self.backend.get("htica_full_gram_max_features", 2048))
+        return (int(lag), 0 if full else F // self.num_subspaces, True)
 
     def compute_cv(self):
         lag = self.configuration.get("lag_time")

@@ -547,6 +547,56 @@ def test_calculators_match_float64_oracle_on_synthetic(dev, tmp_path, engine):
         np.testing.assert_allclose(proj.to_numpy(), (P - cm) / cr, atol=1e-4)
 
 
+@pytest.mark.parametrize("cv,n,f", [("tica", 30000, 256), ("pca", 20000, 130), ("htica", 24000, 300)])
+def test_streamed_load_with_speculative_sums_matches_resident_path(dev, tmp_path, cv, n, f):
+    """Host tensor in: the matrix is copied in chunks and the covariance sums are accumulated
+    under first-chunk standardisation while the copy runs, then corrected exactly.  The weights
+    must equal those of the resident path (device tensor in, sums taken after the statistics)."""
+    from deep_cartograph_b200.modules.cv_learning.cv_calculator import cv_calculators_map
+    X = torch.from_numpy(synth_features(n, f, seed=n + f))
+    cfg = {"dimension": 3, "lag_time": 5, "features_normalization": "mean_std", "num_subspaces": 3,
+           "subspaces_dimension": 4, "backend": {"h2d_chunk_bytes": 4 * f * 4096}}
+    a = cv_calculators_map[cv](configuration=cfg, output_path=str(tmp_path / "a"))
+    a.load_training_tensor(X.pin_memory())
+    assert a._spec is not None and a._spec["rows_done"] == n
+    a.cv_dimension = 3
+    a.compute_cv()
+    assert a._spec is None                                       # consumed
+    b = cv_calculators_map[cv](configuration=cfg, output_path=str(tmp_path / "b"))
+    b.load_training_tensor(X.to(dev))
+    assert b._spec is None
+    b.cv_dimension = 3
+    b.compute_cv()
+    np.testing.assert_array_equal(a.features_norm_mean, b.features_norm_mean)
+    np.testing.assert_array_equal(a.features_norm_range, b.features_norm_range)
+    np.testing.assert_allclose(a.cv, b.cv, atol=2e-5)
+
+
+def test_speculative_sums_are_discarded_when_provisional_statistics_are_off(dev, tmp_path):
+    """The guard: provisional parameters far from the final ones (here: forced) make the calculator
+    drop the speculative sums and recompute on the resident matrix; results match the float64
+    oracle either way."""
+    from deep_cartograph_b200.modules.cv_learning.cv_calculator import TICACalculator
+    n, f = 20000, 130
+    X = synth_features(n, f, seed=9)
+    cfg = {"dimension": 2, "lag_time": 4, "features_normalization": "mean_std",
+           "backend": {"h2d_chunk_bytes": 4 * f * 2048}}
+    calc = TICACalculator(configuration=cfg, output_path=str(tmp_path))
+    calc.load_training_tensor(torch.from_numpy(X).pin_memory())
+    assert calc._spec is not None
+    m0, r0 = calc._spec["norm0"]
+    calc._spec["norm0"] = (m0 + 3.0 * r0, r0)                  # as if the sample had been 3 sigma off
+    mean, rng = calc._norm_on_device()
+    spec = dict(calc._spec)
+    assert calc._take_speculative_sums(calc.training_data, 4, 0, True, mean, rng, None) is None
+    calc._spec = spec
+    calc.cv_dimension = 2
+    calc.compute_cv()
+    Z = oracle.standardize(X, calc.features_norm_mean.astype(np.float32), calc.features_norm_range.astype(np.float32))
+    evals, V = oracle.tica(Z, 4, 2)
+    np.testing.assert_allclose(calc.cv, V, atol=1e-5)
+
+
 def test_traj_cluster_step_api_kmeans(dev, c1, tmp_path):
     from deep_cartograph_b200.tools import traj_cluster
     csv = tmp_path / "tica.csv"
