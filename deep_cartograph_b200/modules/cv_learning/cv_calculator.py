@@ -663,10 +663,229 @@ class HTICACalculator(LinearCalculator):
         return T1 @ V2
 
 
+class DeepTICACalculator(CVCalculator):
+    """DeepTICA (reference ``NonLinear`` + ``DeepTICACalculator``, cv_calculator.py:1038-1891,
+    2517-2611): a feed-forward network trained on time-lagged pairs with the loss
+    ``-sum lambda_i^2`` of the Cholesky-reduced eigenvalues of the minibatch C0 / C_tau (mlcolvar
+    ``DeepTICA.training_step``), whose correlation sums run in ``dcg_ticacov_f32``.
+
+    The reference drives mlcolvar through a lightning ``Trainer``; here the loop is plain PyTorch
+    with the same knobs (``architecture.encoder``, ``training.general`` / ``early_stopping`` /
+    ``optimizer`` / ``model_to_save``, ``tica_regularization``) and the same decisions: ``num_tries``
+    seeded trainings (seed + try), random train/validation split by ``lengths``, validation every
+    ``check_val_every_n_epoch`` epochs, early stopping on ``valid_loss`` (patience, min_delta), best
+    or last weights, a try rejected when its score is below -d (impossible for autocorrelations).
+    The matrix stays resident on the device and minibatches are gathered there (raw features;
+    ``norm_in`` is part of the model, reference :1366-1374).  The linear TICA read-out is fitted on
+    the whole training set (the reference keeps the last minibatch's), then the outputs are min-max
+    normalised to [-1, 1] (:1735-1754).  Training results are seed-dependent in the reference too
+    (unpinned); what is pinned is the arithmetic of the loss (tests) and the model graph."""
+
+    def __init__(self, configuration: Optional[Dict] = None, output_path: Optional[str] = None):
+        super().__init__(configuration, output_path)
+        self.cv_name = "deep_tica"
+        tr = self.configuration.get("training") or {}
+        g = tr.get("general") or {}
+        self.num_tries = int(g.get("num_tries", 10))
+        self.seed = int(g.get("seed", 42))
+        self.lengths = list(g.get("lengths", [0.8, 0.2]))
+        self.batch_size = int(g.get("batch_size", 32))
+        self.max_epochs = int(g.get("max_epochs", 1000))
+        self.shuffle = bool(g.get("shuffle", False))
+        self.random_split = bool(g.get("random_split", True))
+        self.check_val_every = max(1, int(g.get("check_val_every_n_epoch", 10)))
+        es = tr.get("early_stopping") or {}
+        self.patience = int(es.get("patience", 20))
+        self.min_delta = float(es.get("min_delta", 1e-5))
+        opt = tr.get("optimizer") or {}
+        self.opt_name = opt.get("name", "Adam")
+        self.opt_kwargs = dict(opt.get("kwargs") or {"lr": 1e-4, "weight_decay": 0.0})
+        self.model_to_save = tr.get("model_to_save", "best")
+        enc = (self.architecture_config.get("encoder") or {})
+        self.hidden_layers = list(enc.get("layers", [64, 32, 16]))
+        act = enc.get("activation", "leaky_relu")
+        self.activation = (act[0] if isinstance(act, (list, tuple)) and act else act) or "leaky_relu"
+        self.reg = float(self.configuration.get("tica_regularization", 1e-6))
+        self.best_score: Optional[float] = None
+        self.tries_report: List[Dict] = []
+
+    def get_cv_type(self) -> str:
+        return "non-linear"
+
+    # ---- training ---------------------------------------------------------------------------------
+    def _split(self, M: int, gen: torch.Generator):
+        n_train = int(M * self.lengths[0])
+        if self.random_split:
+            perm = torch.randperm(M, generator=gen)
+        else:
+            perm = torch.arange(M)
+        return perm[:n_train], perm[n_train:]
+
+    def _epoch_batches(self, idx: torch.Tensor, gen: torch.Generator, shuffle: bool):
+        if shuffle:
+            idx = idx[torch.randperm(idx.numel(), generator=gen)]
+        bs = self.batch_size
+        for s0 in range(0, idx.numel(), bs):
+            yield idx[s0:s0 + bs]
+
+    def train(self) -> bool:
+        from .deep_tica import DeepTICA
+        X = self.training_data
+        dev = X.device
+        lag = int(self.configuration.get("lag_time") or 1)
+        M = X.shape[0] - lag
+        if M < 4:
+            logger.error("Not enough frames to build time-lagged pairs.")
+            return False
+        mean, rng = self._norm_on_device()
+        d = self.cv_dimension
+        layers = [self.num_features] + self.hidden_layers + [d]
+        n_train = int(M * self.lengths[0])
+        if self.batch_size >= n_train:                       # reference check_batch_size (:1297-1310)
+            self.batch_size = 1 << max(0, (n_train.bit_length() - 1))
+            logger.warning(f"Batch size larger than the training set; using {self.batch_size}")
+        best = None
+        for attempt in range(1, self.num_tries + 1):
+            seed = self.seed + attempt
+            torch.manual_seed(seed)
+            gen = torch.Generator().manual_seed(seed)
+            model = DeepTICA(layers, mean, rng, activation=self.activation, reg=self.reg).to(dev)
+            opt = getattr(torch.optim, self.opt_name)(model.nn.parameters(), **self.opt_kwargs)
+            tr_idx, va_idx = self._split(M, gen)
+            tr_idx, va_idx = tr_idx.to(dev), va_idx.to(dev)
+            best_val, best_state, bad, last_val = float("inf"), None, 0, None
+            history = []
+            for epoch in range(self.max_epochs):
+                model.train()
+                tot, nb = 0.0, 0
+                for b in self._epoch_batches(tr_idx, gen, self.shuffle):
+                    if b.numel() <= d + 1:
+                        continue
+                    loss, _ = model.loss(X[b], X[b + lag])
+                    opt.zero_grad(set_to_none=True)
+                    loss.backward()
+                    opt.step()
+                    tot += float(loss.detach()); nb += 1
+                if (epoch + 1) % self.check_val_every:
+                    continue
+                model.eval()
+                with torch.no_grad():
+                    vt, vn = 0.0, 0
+                    for b in self._epoch_batches(va_idx, gen, False):
+                        if b.numel() <= d + 1:
+                            continue
+                        vl, _ = model.loss(X[b], X[b + lag])
+                        vt += float(vl); vn += 1
+                last_val = vt / max(vn, 1)
+                history.append({"epoch": epoch + 1, "train_loss": tot / max(nb, 1), "valid_loss": last_val})
+                if last_val < best_val - self.min_delta:
+                    best_val, bad = last_val, 0
+                    best_state = {k: v.detach().clone() for k, v in model.state_dict().items()}
+                else:
+                    bad += 1
+                    if bad >= self.patience:
+                        break
+            if last_val is None:                             # never validated: validate once
+                model.eval()
+                with torch.no_grad():
+                    last_val = float(model.loss(X[va_idx], X[va_idx + lag])[0]) if va_idx.numel() > d + 1 else float("nan")
+                best_val = last_val
+            score = best_val if self.model_to_save == "best" else last_val
+            ok = bool(np.isfinite(score)) and score >= -float(d) - 1e-6      # reference :1624-1626
+            self.tries_report.append({"try": attempt, "seed": seed, "score": score, "accepted": ok,
+                                      "epochs": len(history) * self.check_val_every})
+            if not ok:
+                logger.warning(f"DeepTICA try {attempt}: score {score} rejected")
+                continue
+            if self.model_to_save == "best" and best_state is not None:
+                model.load_state_dict(best_state)
+            if best is None or score < best[0]:
+                best = (score, model)
+        if best is None:
+            logger.error("DeepTICA training failed in every try.")
+            return False
+        self.best_score, self.cv = best
+        self.cv.eval()
+        return True
+
+    def compute_cv(self):
+        if self.training_data is None:
+            logger.error("No training data available to train DeepTICA.")
+            return
+        if not self.train():
+            self.cv = None
+            return
+        # linear TICA read-out from the whole training set, streamed in batches (FP64 raw sums)
+        X, lag = self.training_data, int(self.configuration.get("lag_time") or 1)
+        M = X.shape[0] - lag
+        acc = None
+        with torch.no_grad():
+            for s0 in range(0, M, 1 << 16):
+                e0 = min(M, s0 + (1 << 16))
+                s = ops.ticacov_sums(self.cv.features(X[s0:e0]), self.cv.features(X[s0 + lag:e0 + lag]))
+                acc = s if acc is None else {k: acc[k] + s[k] for k in s}
+            evals, V = linalg.tica_from_sums(acc["sff"], acc["sfg"], acc["swf"], acc["slg"], M,
+                                             self.cv_dimension, self.reg)
+            self.cv.tica_mean.copy_((acc["swf"] / M).to(torch.float32))
+            self.cv.tica_evecs.copy_(V.to(torch.float32))
+        self.eigenvalues = evals.cpu().numpy()
+        logger.info(f"DeepTICA eigenvalues: {self.eigenvalues}")
+
+    # ---- projection (reference :1735-1754, 1842-1891) ------------------------------------------
+    @torch.no_grad()
+    def _forward(self, X: torch.Tensor) -> torch.Tensor:
+        out = torch.empty((X.shape[0], self.cv_dimension), dtype=torch.float32, device=X.device)
+        for s0 in range(0, X.shape[0], 1 << 16):
+            out[s0:s0 + (1 << 16)] = self.cv(X[s0:s0 + (1 << 16)])
+        return out
+
+    def normalize_cv(self) -> torch.Tensor:
+        self.cv.out_mean.zero_()
+        self.cv.out_range.fill_(1.0)
+        P = self._forward(self.training_data)
+        mn, mx = P.min(dim=0).values, P.max(dim=0).values
+        if self.shards is not None:
+            mn, mx = self.shards.allreduce_minmax(mn, mx)
+        self.cv.out_mean.copy_((mx + mn) / 2)
+        rg = (mx - mn) / 2
+        self.cv.out_range.copy_(torch.where(rg.abs() < 1e-8, torch.ones_like(rg), rg))
+        self.cv_stats = {"min": mn.cpu().numpy(), "max": mx.cpu().numpy()}
+        return (P - self.cv.out_mean) / self.cv.out_range
+
+    def project_data(self, data: torch.Tensor, normalize_data: bool = True) -> torch.Tensor:
+        if self.cv is None:
+            raise ValueError("No model to project with. Train or load the CV first.")
+        dev = next(self.cv.buffers()).device
+        return self._forward(data.to(dev, torch.float32))
+
+    def get_cv_parameters(self) -> Dict:
+        return {"cv_name": self.cv_name, "cv_dimension": self.cv_dimension,
+                "features_norm_mode": self.feats_norm_mode, "weights_path": getattr(self, "weights_path", None)}
+
+    def save_model(self):
+        """model.zip: metadata, feature labels and the TorchScript module ``cv_weights.pt``
+        (reference :1773-1806; loader :1147-1152)."""
+        super().save_model()
+        f = self.model_output_folder
+        self.weights_path = os.path.join(f, "cv_weights.pt")
+        example = self.training_data[:2].detach()
+        torch.jit.trace(self.cv, example).save(self.weights_path)
+        model_path = os.path.join(self.output_path, "model.zip")
+        zip_files(model_path, str(f))
+        shutil.rmtree(f)
+        logger.info(f"Model saved to {model_path}")
+
+    def _load_from_folder(self, folder_path: str):
+        super()._load_from_folder(folder_path)
+        self.cv = torch.jit.load(os.path.join(self.model_output_folder, "cv_weights.pt"),
+                                 map_location=_device(self.configuration))
+
+
 cv_calculators_map = {
     "pca": PCACalculator,
     "tica": TICACalculator,
     "htica": HTICACalculator,
+    "deep_tica": DeepTICACalculator,
 }
 
 cv_names_map = {"pca": "PCA", "tica": "TICA", "htica": "HTICA", "deep_tica": "DeepTICA"}

@@ -597,6 +597,42 @@ def test_speculative_sums_are_discarded_when_provisional_statistics_are_off(dev,
     np.testing.assert_allclose(calc.cv, V, atol=1e-5)
 
 
+def test_deeptica_calculator_trains_projects_and_round_trips(dev, tmp_path):
+    """DeepTICACalculator (reference NonLinear / DeepTICA protocol): training on the fused minibatch
+    loss improves the validation score, the slow mode of a synthetic series is recovered (leading
+    eigenvalue close to linear TICA's), projections are min-max normalised to [-1, 1], and the
+    TorchScript model.zip reproduces them after CVCalculator.load."""
+    from deep_cartograph_b200.modules.cv_learning.cv_calculator import CVCalculator, cv_calculators_map
+    n, f, lag = 6000, 24, 5
+    X = synth_features(n, f, seed=21, n_slow=3)
+    cfg = {"dimension": 2, "lag_time": lag, "features_normalization": "mean_std", "tica_regularization": 1e-6,
+           "architecture": {"encoder": {"layers": [16, 8], "activation": ["tanh", "tanh"]}},
+           "training": {"general": {"num_tries": 2, "seed": 3, "lengths": [0.8, 0.2], "batch_size": 512,
+                                    "max_epochs": 40, "shuffle": True, "random_split": True,
+                                    "check_val_every_n_epoch": 4},
+                        "early_stopping": {"patience": 5, "min_delta": 1e-5},
+                        "optimizer": {"name": "Adam", "kwargs": {"lr": 5e-3}}, "model_to_save": "best"}}
+    calc = cv_calculators_map["deep_tica"](configuration=cfg, output_path=str(tmp_path))
+    calc.load_training_tensor(torch.from_numpy(X).to(dev), [f"f{i}" for i in range(f)])
+    df = calc.run(2)
+    assert df is not None and list(df.columns) == ["DeepTIC 1", "DeepTIC 2"]
+    assert len(calc.tries_report) == 2 and any(t["accepted"] for t in calc.tries_report)
+    assert -2.0 - 1e-6 <= calc.best_score < -0.5                     # -sum lambda^2 with lambda_1 ~ 0.98
+    P = df.to_numpy()
+    np.testing.assert_allclose(P.min(axis=0), -1.0, atol=1e-5)
+    np.testing.assert_allclose(P.max(axis=0), 1.0, atol=1e-5)
+    # linear TICA of the same data: the network's leading eigenvalue must not be far below it
+    Z = oracle.standardize(X, calc.features_norm_mean.astype(np.float32), calc.features_norm_range.astype(np.float32))
+    ev_lin, _ = oracle.tica(Z, lag, 2)
+    assert calc.eigenvalues[0] > ev_lin[0] - 0.05
+    model_zip = os.path.join(str(tmp_path), "deep_tica", "model.zip")
+    assert os.path.exists(model_zip)
+    again = CVCalculator.load(model_zip, str(tmp_path / "reload"))
+    assert again.get_cv_type() == "non-linear" and again.get_labels() == ["DeepTIC 1", "DeepTIC 2"]
+    P2 = again.project_data(torch.from_numpy(X)).cpu().numpy()
+    np.testing.assert_allclose(P2, P, atol=2e-5)
+
+
 def test_traj_cluster_step_api_kmeans(dev, c1, tmp_path):
     from deep_cartograph_b200.tools import traj_cluster
     csv = tmp_path / "tica.csv"
