@@ -45,7 +45,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--engine", default=os.environ.get("DCG_COV_ENGINE", "tc_3xtf32"))
+    ap.add_argument("--engine", default=os.environ.get("DCG_COV_ENGINE", "tc_3xf16"),
+                    choices=["tc_3xf16", "tc_3xtf32", "tc_1xtf32", "simt_f32"])
     ap.add_argument("--frames", type=int, default=N_PER_GPU, help="frames per GPU (default = C2)")
     ap.add_argument("--features", type=int, default=F)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -299,20 +300,24 @@ def main():
     # ---- roofline of the dominant kernel (covariance contraction)
     M = n - LAG if world == 1 else n            # pairs per rank (last rank has n - lag)
     alg_flops = 3.0 * f * f * M                  # 2F^2 (C_tau) + F^2 (upper C0) per pair
-    tf32_peak = peaks["bf16_tflops"] / 2.0       # dense TF32 = 1/2 of dense bf16 on the tcgen05 pipe
+    # peak of the chosen tensor-core precision: kind::f16 = the measured bf16 figure; dense TF32 is
+    # 1/2 of it on the tcgen05 pipe (K = 8 instead of 16 per instruction, same cycles)
+    f16_kind = engine == "tc_3xf16"
+    tf32_peak = peaks["bf16_tflops"] if f16_kind else peaks["bf16_tflops"] / 2.0
     cov_s = float(cov_ms.item()) * 1e-3
     achieved = alg_flops / cov_s / 1e12
-    issued_mult = {"tc_3xtf32": 3.0, "tc_1xtf32": 1.0, "simt_f32": 1.0}[engine]
+    issued_mult = {"tc_3xf16": 3.0, "tc_3xtf32": 3.0, "tc_1xtf32": 1.0, "simt_f32": 1.0}[engine]
     # DRAM bytes per launch of this kernel at this shape, from the committed ncu --set full capture
     # (profiles/r1_cov_tc_v2_ncu_summary.txt: dram__bytes_read.sum + dram__bytes_write.sum)
-    traffic = 9.95e9 if (engine == "tc_3xtf32" and n == N_PER_GPU and f == F) else None
+    traffic = 9.95e9 if (engine in ("tc_3xtf32", "tc_3xf16") and n == N_PER_GPU and f == F) else None
     roofline = {"bound": "tensor", "kernel": f"cov_lag ({engine})", "achieved": achieved, "peak": tf32_peak,
                 "unit": "TFLOP/s", "frac": achieved / tf32_peak, "traffic": traffic,
                 "traffic_note": "bytes/launch (ncu); algorithmic bytes/launch = 4*F*n = %.3g" % (4.0 * f * n),
                 "issued_tflops": achieved * issued_mult, "frac_issued": achieved * issued_mult / tf32_peak,
                 "kernel_ms": cov_s * 1e3, "share_of_step": cov_s * 1e3 / ms_per_step,
-                "peak_source": f"{peaks['source']} bf16 burst / 2 (TF32 : bf16 = 1 : 2 on tcgen05)",
-                "algorithmic": "3*F^2 FLOP per frame pair; issued = x3 for 3xTF32"}
+                "peak_source": (f"{peaks['source']} bf16 burst (kind::f16)" if f16_kind else
+                                f"{peaks['source']} bf16 burst / 2 (TF32 : bf16 = 1 : 2 on tcgen05)"),
+                "algorithmic": "3*F^2 FLOP per frame pair; issued = x3 for the split-precision engines"}
 
     # ---- per-pass device times and the HBM fractions of the memory-bound passes (SURVEY 8d bytes)
     def _avg_ms(name):
@@ -381,7 +386,8 @@ def main():
         line = {"metric": "frames/s, TICA C0/Ctau + projection + KMeans (hot path)", "value": value,
                 "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32 (tf32x3 tensor contraction, f64 accumulation)" if engine == "tc_3xtf32" else "f32",
+                "dtype": {"tc_3xf16": "f32 (f16x3 split-precision tensor contraction, f64 accumulation)",
+                          "tc_3xtf32": "f32 (tf32x3 split-precision tensor contraction, f64 accumulation)"}.get(engine, "f32"),
                 "data": "synthetic", "config": workload_config(args, world, engine),
                 "roofline": roofline, "passes": passes, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
                 "clocks": clocks, "eigenvalues": [float(v) for v in evals.cpu().tolist()]}

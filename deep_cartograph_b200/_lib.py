@@ -18,7 +18,9 @@ _p = C.c_void_p
 COV_SIMT_F32 = 0
 COV_TC_3XTF32 = 1
 COV_TC_1XTF32 = 2
-COV_ENGINES = {"simt_f32": COV_SIMT_F32, "tc_3xtf32": COV_TC_3XTF32, "tc_1xtf32": COV_TC_1XTF32}
+COV_TC_3XF16 = 3
+COV_ENGINES = {"simt_f32": COV_SIMT_F32, "tc_3xtf32": COV_TC_3XTF32, "tc_1xtf32": COV_TC_1XTF32,
+               "tc_3xf16": COV_TC_3XF16}
 
 _SIGNATURES = {
     # name: (restype, [argtypes])

@@ -210,7 +210,8 @@ extern "C" int dcg_cov_lag_f32(const float* X, int64_t n_rows, int f, int64_t ld
   if (!X || (!S0 && !St)) return DCG_E_NULL;
   if ((mean == nullptr) != (range == nullptr)) return DCG_E_NULL;
   if (n_rows <= 0 || f <= 0 || ld < f || lag < 0 || lag >= n_rows || block < 0) return DCG_E_SHAPE;
-  if (engine != DCG_COV_SIMT_F32 && engine != DCG_COV_TC_3XTF32 && engine != DCG_COV_TC_1XTF32)
+  if (engine != DCG_COV_SIMT_F32 && engine != DCG_COV_TC_3XTF32 && engine != DCG_COV_TC_1XTF32 &&
+      engine != DCG_COV_TC_3XF16)
     return DCG_E_MODE;
   if (!ws || ws_bytes < dcg_cov_workspace_bytes(n_rows, f, lag, block, engine)) return DCG_E_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;

@@ -1,4 +1,4 @@
-// tcgen05 covariance engine, CTA-pair edition (DCG_COV_TC_3XTF32 / DCG_COV_TC_1XTF32).
+// tcgen05 covariance engine, CTA-pair edition (DCG_COV_TC_3XTF32 / DCG_COV_TC_1XTF32 / DCG_COV_TC_3XF16).
 //
 // Computes, for 256 x 256 super-tiles (I, J) of the feature axis and a range of frames,
 //     S0[I,J] += sum_t z_t[I] (x) z_t[J]        or        St[I,J] += sum_t z_t[I] (x) z_{t+lag}[J]
@@ -20,7 +20,12 @@
 // the 16-byte stores of a warp contiguous, i.e. bank-conflict free); the epilogue undoes it.
 // Row strides that are not a multiple of 4 floats fall back to 8- or 4-byte loads (VEC = 2, 1).
 //
-// Precision.  3xTF32: D += Ahi*Bhi + Ahi*Blo + Alo*Bhi.  The tensor core adds into its FP32
+// Precision.  3xF16 (DCG_COV_TC_3XF16): the same split with FP16 pieces (hi = RN_f16(z),
+// lo = RN_f16(z - hi); FP16 and TF32 both carry 11 significant bits, so the split is as accurate
+// as long as |z| < 65504 and 6e-8 absolute is negligible -- true for standardised features) on
+// kind::f16, whose K is 16: half the MMA instructions per frame.  A producer thread then converts
+// 8 frames x 4 features per visit and a pipeline stage holds 32 frames in the same 32 KB.
+// 3xTF32: D += Ahi*Bhi + Ahi*Blo + Alo*Bhi.  The tensor core adds into its FP32
 // accumulator with truncation (measured: -5e-8 relative per MMA on same-sign sums), so
 // accumulation is two-level: the level-1 accumulator (TMEM columns [0,256)) takes `kc` frames
 // (default 256: 2.4e-6 relative to float64, measured; DCG_TC_KC overrides), then the epilogue warps
@@ -39,6 +44,7 @@
 // upper triangle of S0); issued MMA FLOPs = 3x that for 3xTF32.  X is re-read once per super-tile
 // row and column from L2 (work items of the same frame range run concurrently).
 #include <cstdlib>
+#include <cuda_fp16.h>
 #include "dcg_common.cuh"
 #include "cov_engines.cuh"
 #include "tc_common.cuh"
@@ -51,7 +57,13 @@ namespace {
 
 constexpr int kSup = 256;            // super-tile edge = UMMA M = N (features)
 constexpr int kHalf = 128;           // operand rows staged per CTA
-constexpr int kStage = 16;           // frames per pipeline stage (two K = 8 MMA steps)
+// precision modes of the contraction
+constexpr int kPrecTf32x1 = 0, kPrecTf32x3 = 1, kPrecF16x3 = 2;
+// frames per pipeline stage = two MMA K-steps: kind::tf32 has K = 8 (16 frames), kind::f16 K = 16
+// (32 frames).  The shared-memory geometry is the same in both: 16-byte K-groups (4 x tf32 or
+// 8 x f16), four groups per operand plane.
+__host__ __device__ constexpr int stage_frames(int prec) { return prec == kPrecF16x3 ? 32 : 16; }
+constexpr int kStageMin = 16;
 constexpr int kNS = 6;               // pipeline stages
 constexpr int kSets = 2;              // producer warp sets; set k stages the item's stages k, k + kSets, ...
 constexpr int kSetWarps = 8;         // warps per set: 4 per operand (one per 4-frame group of the stage)
@@ -59,8 +71,8 @@ constexpr int kProdWarps = kSets * kSetWarps;
 constexpr int kEpiWarps = 4;
 constexpr int kMmaWarp = kProdWarps;
 constexpr int kThreads = (kProdWarps + kEpiWarps) * 32;       // 640: 5 warps per scheduler, 96 registers
-constexpr int kGroupBytes = kHalf * 16;                       // one 4-frame group of 128 rows
-constexpr int kPlaneBytes = (kStage / 4) * kGroupBytes;       // 8 KB: one operand plane (hi or lo)
+constexpr int kGroupBytes = kHalf * 16;                       // one K-group (16 bytes) of 128 rows
+constexpr int kPlaneBytes = 4 * kGroupBytes;                  // 8 KB: one operand plane (hi or lo)
 constexpr int kStageBytes = 4 * kPlaneBytes;                  // A_hi A_lo B_hi B_lo
 constexpr size_t kSmemBytes = (size_t)kNS * kStageBytes + 1024;
 constexpr int kMaxItemFrames = 16384;                         // level-2 FP32 accumulation span
@@ -187,6 +199,23 @@ __device__ __forceinline__ void mma2_tf32_ss(uint32_t d_tmem, uint64_t a_desc, u
       "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void mma2_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+template <bool F16>
+__device__ __forceinline__ void mma2_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                        uint32_t idesc, uint32_t accumulate) {
+  if constexpr (F16) mma2_f16_ss(d_tmem, a_desc, b_desc, idesc, accumulate);
+  else mma2_tf32_ss(d_tmem, a_desc, b_desc, idesc, accumulate);
+}
+// kind::f16 instruction descriptor: FP16 operands (format 0), FP32 accumulate, both K-major, dense
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 // the barrier at this offset in BOTH CTAs gets one arrival when all MMAs issued so far are done
 __device__ __forceinline__ void mma2_commit_both(uint64_t* bar) {
   asm volatile(
@@ -209,8 +238,12 @@ __device__ __forceinline__ void load_row4(const float* p, float* x) {
   }
 }
 
-template <bool X3, int VEC>
+template <int PREC, int VEC>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) cov_tc_kernel(const Params p) {
+  constexpr bool X3 = PREC != kPrecTf32x1;
+  constexpr bool F16 = PREC == kPrecF16x3;
+  constexpr int kStage = stage_frames(PREC);
+  constexpr int kRows = kStage / 4;                // frames per producer thread block (4 or 8)
   extern __shared__ unsigned char smem_raw[];
   // identical offsets in both CTAs (the dynamic window starts at the same shared address)
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -253,7 +286,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) cov_tc_
       // =============================== producers ==============================================
       const int set = warp / kSetWarps;                // this warp stages the item's stages set, set + kSets, ...
       const int op = (warp >> 2) & 1;                  // 0 = A (z_t[I]), 1 = B (z_t[J] or z_{t+lag}[J])
-      const int g = warp & 3;                          // 4-frame group of the stage
+      const int g = warp & 3;                          // K-group of the stage (kRows frames)
       const bool needed = op == 0 || !td.diag;
       const int c = (op == 0 ? td.i0 : td.j0) + (int)rank * kHalf + 4 * lane;   // first of 4 features
       const int c_lo = op == 0 ? td.i_lo : td.j_lo, c_hi = op == 0 ? td.i_hi : td.j_hi;
@@ -271,15 +304,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) cov_tc_
       // zero (also what the column sums need); B rows only need to be in bounds.
       const int t_lim = (int)((op == 0 || td.diag ? f1 : p.n_rows - shift) - f0);
       const size_t ld = (size_t)p.ld;
-      const float* pst = p.X + (size_t)(f0 + shift + set * kStage + 4 * g) * ld + c;   // this thread's first block
+      const float* pst = p.X + (size_t)(f0 + shift + set * kStage + kRows * g) * ld + c;   // this thread's first block
       // x[4 * r + v] = frame (t0 + r), feature (c + v)
-      auto load_block = [&](float (&x)[16], int t0, const float* pt) {
-        if (all_ok && t0 + 3 < t_lim) {
+      auto load_block = [&](float (&x)[4 * kRows], int t0, const float* pt) {
+        if (all_ok && t0 + kRows - 1 < t_lim) {
 #pragma unroll
-          for (int r = 0; r < 4; ++r) load_row4<VEC>(pt + r * ld, &x[4 * r]);
+          for (int r = 0; r < kRows; ++r) load_row4<VEC>(pt + r * ld, &x[4 * r]);
         } else {
 #pragma unroll
-          for (int r = 0; r < 4; ++r)
+          for (int r = 0; r < kRows; ++r)
 #pragma unroll
             for (int v = 0; v < 4; ++v)
               x[4 * r + v] = (ok[v] && t0 + r < t_lim) ? __ldg(pt + r * ld + v) : mu[v];   // mu -> z == 0 exactly
@@ -287,24 +320,38 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) cov_tc_
       };
       constexpr int kStep = kSets * kStage;                 // frames between this warp's stages
       const size_t step_stride = (size_t)kStep * ld;
-      int t0 = set * kStage + 4 * g;
+      int t0 = set * kStage + kRows * g;
       uint32_t s = (uint32_t)set;
       if (needed) {
         const uint32_t dst0 = smem_base + (uint32_t)(2 * op) * kPlaneBytes + (uint32_t)g * kGroupBytes + (uint32_t)lane * 16;
         // standardise, split, store K-major, publish the stage
-        auto emit_block = [&](const float (&x)[16], uint32_t g_stage) {
+        auto emit_block = [&](const float (&x)[4 * kRows], uint32_t g_stage) {
           const uint32_t slot = g_stage % kNS;
           mbar_wait(&empty_bar[slot], ((g_stage / kNS) & 1) ^ 1);
           const uint32_t dst = dst0 + slot * kStageBytes;
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
             uint32_t hi[4], lo[4];
+            if constexpr (F16) {
+              // 8 frames of one feature -> 8 x f16 hi (RN) and 8 x f16 lo = RN(z - hi), packed in pairs
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-              // (x - mean) * RN(1/range): within 1 ulp of the reference's IEEE division (the
-              // difference is a per-feature scale factor of at most 1 + 2^-24)
-              const float z = (x[4 * r + v] - mu[v]) * ri[v];
-              split_tf32_fast(z, hi[r], lo[r]);
+              for (int r2 = 0; r2 < 4; ++r2) {
+                const float z0 = (x[4 * (2 * r2) + v] - mu[v]) * ri[v];
+                const float z1 = (x[4 * (2 * r2 + 1) + v] - mu[v]) * ri[v];
+                const __half2 h = __floats2half2_rn(z0, z1);
+                const float2 hf = __half22float2(h);
+                const __half2 l = __floats2half2_rn(z0 - hf.x, z1 - hf.y);
+                hi[r2] = *reinterpret_cast<const uint32_t*>(&h);
+                lo[r2] = *reinterpret_cast<const uint32_t*>(&l);
+              }
+            } else {
+#pragma unroll
+              for (int r = 0; r < 4; ++r) {
+                // (x - mean) * RN(1/range): within 1 ulp of the reference's IEEE division (the
+                // difference is a per-feature scale factor of at most 1 + 2^-24)
+                const float z = (x[4 * r + v] - mu[v]) * ri[v];
+                split_tf32_fast(z, hi[r], lo[r]);
+              }
             }
             st_shared_v4(dst + v * 512, hi[0], hi[1], hi[2], hi[3]);                 // operand row v * 32 + lane
             if (X3) st_shared_v4(dst + kPlaneBytes + v * 512, lo[0], lo[1], lo[2], lo[3]);
@@ -313,23 +360,38 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) cov_tc_
           __syncwarp();
           if (lane == 0) mbar_arrive_cta(&full_bar[slot], 0);
         };
-        // software pipeline: the loads of this warp's next stage are in flight while the current one
-        // is converted (and the other warp set works on the stages in between)
-        float xa[16], xb[16];
-        if (s < nS) load_block(xa, t0, pst);
-        for (; s + kSets < nS; s += 2 * kSets) {
-          load_block(xb, t0 + kStep, pst + step_stride);
-          emit_block(xa, gs + s);
-          if (s + 2 * kSets < nS) load_block(xa, t0 + 2 * kStep, pst + 2 * step_stride);
-          emit_block(xb, gs + s + kSets);
-          t0 += 2 * kStep;
-          pst += 2 * step_stride;
+        if constexpr (F16) {
+          // 8 frames x 4 features per thread in ONE buffer: the loads of the warp's next stage are
+          // issued right after the current stage is published, so they fly while the warp waits for
+          // its next slot (the other warp set works in between) and nothing is in flight at the
+          // proxy fence (its MEMBAR would wait for it)
+          float xa[4 * kRows];
+          if (s < nS) load_block(xa, t0, pst);
+          for (; s < nS; s += kSets) {
+            emit_block(xa, gs + s);
+            t0 += kStep;
+            pst += step_stride;
+            if (s + kSets < nS) load_block(xa, t0, pst);
+          }
+        } else {
+          // software pipeline: the loads of this warp's next stage are in flight while the current
+          // one is converted (and the other warp set works on the stages in between)
+          float xa[4 * kRows], xb[4 * kRows];
+          if (s < nS) load_block(xa, t0, pst);
+          for (; s + kSets < nS; s += 2 * kSets) {
+            load_block(xb, t0 + kStep, pst + step_stride);
+            emit_block(xa, gs + s);
+            if (s + 2 * kSets < nS) load_block(xa, t0 + 2 * kStep, pst + 2 * step_stride);
+            emit_block(xb, gs + s + kSets);
+            t0 += 2 * kStep;
+            pst += 2 * step_stride;
+          }
+          if (s < nS) emit_block(xa, gs + s);
         }
-        if (s < nS) emit_block(xa, gs + s);
       } else {
         // Diagonal S0 tile: B is A, so the B warps have nothing to stage.  They keep the pipeline
         // protocol and, if asked, accumulate the column sums sum_t z_t of the tile's features (same
-        // rows and bounds as the A operand) -- FP32 within a 4-frame block, FP64 across blocks.
+        // rows and bounds as the A operand) -- FP32 within a block of frames, FP64 across blocks.
         const bool want_sum = p.colsum != nullptr;
         double zsum[4] = {0.0, 0.0, 0.0, 0.0};
         for (; s < nS; s += kSets, t0 += kStep, pst += step_stride) {
@@ -338,13 +400,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) cov_tc_
           __syncwarp();
           if (lane == 0) mbar_arrive_cta(&full_bar[slot], 0);
           if (want_sum) {
-            float x[16];
+            float x[4 * kRows];
             load_block(x, t0, pst);
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
               float sv = 0.f;
 #pragma unroll
-              for (int r = 0; r < 4; ++r) sv += (x[4 * r + v] - mu[v]) * ri[v];
+              for (int r = 0; r < kRows; ++r) sv += (x[4 * r + v] - mu[v]) * ri[v];
               zsum[v] += (double)sv;
             }
           }
@@ -365,7 +427,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) cov_tc_
       const int q = warp & 3;                          // TMEM lane quarter this warp may access
       const uint32_t lane_base = (uint32_t)(q * 32) << 16;
       const bool issuer = warp == kMmaWarp && rank == 0;
-      constexpr uint32_t idesc = make_idesc_tf32(kSup, kSup, 0, 0);   // both operands K-major
+      constexpr uint32_t idesc = F16 ? make_idesc_f16(kSup, kSup) : make_idesc_tf32(kSup, kSup, 0, 0);   // both operands K-major
       uint32_t s = 0;
       for (uint32_t c = 0; c < nC; ++c, ++gc) {
         if (issuer) {
@@ -382,12 +444,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) cov_tc_
               const uint64_t b_h0 = td.diag ? a_h0 : make_smem_desc(st_base + 2 * kPlaneBytes, kGroupBytes, 128);
               const uint64_t b_l0 = td.diag ? a_l0 : make_smem_desc(st_base + 3 * kPlaneBytes, kGroupBytes, 128);
 #pragma unroll
-              for (int h = 0; h < kStage / 8; ++h) {
-                const uint64_t off = (uint64_t)((h * 2 * kGroupBytes) >> 4);     // K = 8 = two 4-frame groups
-                mma2_tf32_ss(l1, a_h0 + off, b_h0 + off, idesc, (first && h == 0) ? 0u : 1u);
+              for (int h = 0; h < 2; ++h) {
+                const uint64_t off = (uint64_t)((h * 2 * kGroupBytes) >> 4);     // one K-step = two 16-byte K-groups
+                mma2_ss<F16>(l1, a_h0 + off, b_h0 + off, idesc, (first && h == 0) ? 0u : 1u);
                 if (X3) {
-                  mma2_tf32_ss(l1, a_h0 + off, b_l0 + off, idesc, 1);
-                  mma2_tf32_ss(l1, a_l0 + off, b_h0 + off, idesc, 1);
+                  mma2_ss<F16>(l1, a_h0 + off, b_l0 + off, idesc, 1);
+                  mma2_ss<F16>(l1, a_l0 + off, b_h0 + off, idesc, 1);
                 }
               }
               mma2_commit_both(&empty_bar[slot]);                              // stage consumed
@@ -453,9 +515,9 @@ int env_int(const char* name, int dflt) {
   return s ? atoi(s) : dflt;
 }
 
-template <bool X3, int VEC>
+template <int PREC, int VEC>
 int launch_variant(const Params& p, int64_t n_items, cudaStream_t st) {
-  auto kern = cov_tc_kernel<X3, VEC>;
+  auto kern = cov_tc_kernel<PREC, VEC>;
   DCG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
   const int n_clusters = (int)std::min<int64_t>(kNumSMs / 2, n_items);
   kern<<<2 * n_clusters, kThreads, kSmemBytes, st>>>(p);
@@ -476,8 +538,13 @@ int cov_tc_launch(const CovArgs& a, cudaStream_t st) {
   DCG_CUDA_TRY(cudaGetDevice(&dev));
   DCG_CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
   if (major != 10) return DCG_E_ARCH;
+  const int prec = a.engine == DCG_COV_TC_3XF16 ? kPrecF16x3 : a.engine == DCG_COV_TC_3XTF32 ? kPrecTf32x3 : kPrecTf32x1;
+  const int stage = stage_frames(prec);
+  // kind::f16 adds into the accumulator once per 16 frames (kind::tf32: per 8): at the same chunk
+  // length its truncation error is smaller (1.6e-6 against 2.4e-6 at kc = 256, measured); chunks
+  // twice as long (3.2e-6) gain only 5 % and cost eigenvector accuracy, so both use the same kc
   int kc = env_int("DCG_TC_KC", kDefaultKc);
-  kc = std::max(kStage, kc / kStage * kStage);
+  kc = std::max(stage, kc / stage * stage);
 
   const int64_t M = a.n_rows - a.lag;
   TileDesc* d_tiles = (TileDesc*)((char*)a.ws + 256);
@@ -497,13 +564,15 @@ int cov_tc_launch(const CovArgs& a, cudaStream_t st) {
   if (!cov_tc_fuses_colsums(a)) colsum = nullptr;
   Params p{a.X, a.n_rows, a.ld, a.f, a.lag, a.mean, a.range, a.S0, a.St, colsum,
            d_tiles, n_tiles, g, n_ranges * n_tiles, kc};
-  const bool x3 = a.engine == DCG_COV_TC_3XTF32;
   const int vec = row_vec_width(a.X, a.ld);
   int rc;
-  if (x3) rc = vec == 4 ? launch_variant<true, 4>(p, p.n_items, st) : vec == 2 ? launch_variant<true, 2>(p, p.n_items, st)
-                                                                             : launch_variant<true, 1>(p, p.n_items, st);
-  else rc = vec == 4 ? launch_variant<false, 4>(p, p.n_items, st) : vec == 2 ? launch_variant<false, 2>(p, p.n_items, st)
-                                                                            : launch_variant<false, 1>(p, p.n_items, st);
+#define DCG_TC_VARIANTS(P)                                                                          \
+  rc = vec == 4 ? launch_variant<P, 4>(p, p.n_items, st) : vec == 2 ? launch_variant<P, 2>(p, p.n_items, st) \
+                                                                    : launch_variant<P, 1>(p, p.n_items, st)
+  if (prec == kPrecF16x3) { DCG_TC_VARIANTS(kPrecF16x3); }
+  else if (prec == kPrecTf32x3) { DCG_TC_VARIANTS(kPrecTf32x3); }
+  else { DCG_TC_VARIANTS(kPrecTf32x1); }
+#undef DCG_TC_VARIANTS
   if (rc) return rc;
   if (a.colsum_lag && colsum) {
     tc_colsum_lag_kernel<<<(unsigned)ceil_div(a.f, 128), 128, 0, st>>>(

@@ -53,17 +53,21 @@ def _ws(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
-def default_cov_engine() -> int:
-    """Engine used when none is requested: env DCG_COV_ENGINE or the tcgen05 3xTF32 engine."""
-    name = os.environ.get("DCG_COV_ENGINE", "tc_3xtf32")
+def default_cov_engine(standardised: bool = True) -> int:
+    """Engine used when none is requested: env DCG_COV_ENGINE, else the tcgen05 split-precision
+    engine -- 3xF16 when the kernel standardises the data itself (|z| is then far inside the FP16
+    range; same 11-bit pieces as 3xTF32 at half the MMA count), 3xTF32 for raw inputs."""
+    name = os.environ.get("DCG_COV_ENGINE", "auto")
+    if name == "auto":
+        return COV_ENGINES["tc_3xf16" if standardised else "tc_3xtf32"]
     if name not in COV_ENGINES:
-        raise ValueError(f"DCG_COV_ENGINE={name!r}; choose from {sorted(COV_ENGINES)}")
+        raise ValueError(f"DCG_COV_ENGINE={name!r}; choose from {sorted(COV_ENGINES)} or 'auto'")
     return COV_ENGINES[name]
 
 
-def resolve_engine(engine) -> int:
-    if engine is None:
-        return default_cov_engine()
+def resolve_engine(engine, standardised: bool = True) -> int:
+    if engine is None or engine == "auto":
+        return default_cov_engine(standardised)
     if isinstance(engine, str):
         return COV_ENGINES[engine]
     return int(engine)
@@ -150,7 +154,7 @@ def lagged_covariance(X: torch.Tensor, lag: int, mean: Optional[torch.Tensor] = 
         _need_cuda("range", rng, torch.float32)
         mean = mean.contiguous()
         rng = rng.contiguous()
-    eng = resolve_engine(engine)
+    eng = resolve_engine(engine, standardised=mean is not None)
     lib = _lib.load()
     dev = X.device
     want_st = want_st and lag > 0

@@ -40,6 +40,9 @@ extern "C" {
 #define DCG_COV_SIMT_F32   0 /* CUDA-core FP32 FMA tiles, FP64 flush (validation engine)        */
 #define DCG_COV_TC_3XTF32  1 /* tcgen05 kind::tf32, split precision hi*hi + hi*lo + lo*hi       */
 #define DCG_COV_TC_1XTF32  2 /* tcgen05 kind::tf32, single pass (fast, ~1e-3 relative)          */
+#define DCG_COV_TC_3XF16   3 /* tcgen05 kind::f16, FP16 split hi*hi + hi*lo + lo*hi: same 11-bit
+                                pieces as 3xTF32 at half the MMA count; needs |z| < 65504 (i.e.
+                                standardised inputs)                                            */
 
 int dcg_version(void);
 const char* dcg_error_string(int code);

@@ -18,7 +18,7 @@ from conftest import GOLDEN, synth_features
 
 pytestmark = pytest.mark.gpu
 
-ENGINES = ["simt_f32", "tc_3xtf32"]
+ENGINES = ["simt_f32", "tc_3xtf32", "tc_3xf16"]
 
 
 @pytest.fixture(scope="module")

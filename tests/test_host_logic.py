@@ -235,7 +235,7 @@ def test_schemas_accept_reference_yaml_and_defaults():
                                 "figures": {"fes": {"compute": True}}, "tica": {"lag_time": 3}}).model_dump()
     assert cfg["common"]["num_subspaces"] == 10 and cfg["common"]["subspaces_dimension"] == 5
     assert cfg["common"]["tica_regularization"] == 1e-6 and cfg["tica"] == {"lag_time": 3}
-    assert cfg["common"]["backend"]["cov_engine"] == "tc_3xtf32"
+    assert cfg["common"]["backend"]["cov_engine"] == "auto"
     d = TrajClusterSchema().model_dump()
     assert d["algorithm"] == "hierarchical" and d["search_interval"] == [3, 10] and d["n_init"] == 20
     with pytest.raises(Exception):
