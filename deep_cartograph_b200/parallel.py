@@ -36,8 +36,9 @@ class FrameShards:
 
     # ---- statistics ---------------------------------------------------------------------------
     def merge_stats(self, st: dict) -> dict:
-        """All-gather the per-rank column statistics and Chan-merge them in rank order."""
-        from .ops import merge_column_stats
+        """All-gather the per-rank column statistics and merge them on the device in one shot
+        (FP64): N = sum n_r, mean = sum n_r mean_r / N, M2 = sum M2_r + sum n_r (mean_r - mean)^2,
+        min / max over ranks.  One collective, one host read (the global frame count)."""
         f = st["mean"].numel()
         dev = st["mean"].device
         packed = torch.empty(1 + 4 * f, dtype=torch.float64, device=dev)
@@ -46,14 +47,20 @@ class FrameShards:
         packed[1 + f:1 + 2 * f] = st["m2"]
         packed[1 + 2 * f:1 + 3 * f] = st["min"].to(torch.float64)
         packed[1 + 3 * f:] = st["max"].to(torch.float64)
-        out = [torch.empty_like(packed) for _ in range(self.world)]
-        dist.all_gather(out, packed, group=self.group)
-        parts = []
-        for p in out:
-            parts.append({"n": int(round(float(p[0].item()))), "mean": p[1:1 + f], "m2": p[1 + f:1 + 2 * f],
-                          "min": p[1 + 2 * f:1 + 3 * f].to(torch.float32),
-                          "max": p[1 + 3 * f:].to(torch.float32)})
-        return merge_column_stats(parts)
+        flat = torch.empty(self.world * (1 + 4 * f), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(flat, packed, group=self.group)
+        allp = flat.view(self.world, 1 + 4 * f)
+        n_r = allp[:, 0:1]                                   # (world, 1); empty shards carry n = 0
+        live = n_r > 0
+        N = n_r.sum()
+        mean_r = torch.where(live, allp[:, 1:1 + f], torch.zeros((), dtype=torch.float64, device=dev))
+        mean = (n_r * mean_r).sum(dim=0) / N
+        m2 = (torch.where(live, allp[:, 1 + f:1 + 2 * f], torch.zeros((), dtype=torch.float64, device=dev))
+              + n_r * (mean_r - mean) ** 2).sum(dim=0)
+        inf = torch.full((), float("inf"), dtype=torch.float64, device=dev)
+        mn = torch.where(live, allp[:, 1 + 2 * f:1 + 3 * f], inf).min(dim=0).values.to(torch.float32)
+        mx = torch.where(live, allp[:, 1 + 3 * f:], -inf).max(dim=0).values.to(torch.float32)
+        return {"n": int(round(float(N.item()))), "mean": mean, "m2": m2, "min": mn, "max": mx}
 
     # ---- halo ---------------------------------------------------------------------------------
     def with_halo(self, X: torch.Tensor, lag: int) -> torch.Tensor:
@@ -114,11 +121,11 @@ class FrameShards:
         return out
 
     def allreduce_minmax(self, mn: torch.Tensor, mx: torch.Tensor):
-        mn = mn.clone()
-        mx = mx.clone()
-        dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=self.group)
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=self.group)
-        return mn, mx
+        """Global per-column min and max in ONE collective: MAX over [-min | max]."""
+        d = mn.numel()
+        buf = torch.cat([-mn, mx])
+        dist.all_reduce(buf, op=dist.ReduceOp.MAX, group=self.group)
+        return -buf[:d], buf[d:]
 
     def allreduce_sum_(self, t: torch.Tensor) -> torch.Tensor:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
