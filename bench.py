@@ -259,13 +259,14 @@ def main():
         if shards is not None:
             shards.broadcast_(C, 0)
         labels = torch.full((n,), -1, dtype=torch.int32, device=dev)
+        work = ops.kmeans_work(K, DIM, dev)
         for _ in range(KM_ITERS):
+            if shards is None:
+                ops.kmeans_iterate_(P, C, labels, work)      # one library call per Lloyd iteration
+                continue
             r = ops.kmeans_step(P, C, labels)
-            sums, counts = r["sums"], r["counts"]
-            if shards is not None:
-                packed = shards.allreduce_sum_(torch.cat([sums.reshape(-1), counts]))
-                sums, counts = packed[:K * DIM].view(K, DIM), packed[K * DIM:]
-            ops.kmeans_update_(C, sums.contiguous(), counts.contiguous())
+            packed = shards.allreduce_sum_(torch.cat([r["sums"].reshape(-1), r["counts"]]))
+            ops.kmeans_update_(C, packed[:K * DIM].view(K, DIM), packed[K * DIM:])
       return evals, labels
 
     def sync_all():

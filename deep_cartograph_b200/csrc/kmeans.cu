@@ -363,10 +363,15 @@ extern "C" int dcg_kmeans_step(const void* Y, int64_t n, int d, int64_t ld, int 
   if (n <= 0 || d < 1 || d > 32 || ld < d || k < 1) return DCG_E_SHAPE;
   if (dtype_bytes != 4 && dtype_bytes != 8) return DCG_E_MODE;
   cudaStream_t st = (cudaStream_t)stream;
-  DCG_CUDA_TRY(cudaMemsetAsync(stats, 0, 3 * sizeof(double), st));
-  if (update_sums) {
-    DCG_CUDA_TRY(cudaMemsetAsync(sums, 0, (size_t)k * d * sizeof(double), st));
-    DCG_CUDA_TRY(cudaMemsetAsync(counts, 0, (size_t)k * sizeof(double), st));
+  if (update_sums && counts == sums + (size_t)k * d && stats == counts + k) {
+    // [sums | counts | stats] in one buffer (dcg_kmeans_iterate): one memset
+    DCG_CUDA_TRY(cudaMemsetAsync(sums, 0, ((size_t)k * d + k + 3) * sizeof(double), st));
+  } else {
+    DCG_CUDA_TRY(cudaMemsetAsync(stats, 0, 3 * sizeof(double), st));
+    if (update_sums) {
+      DCG_CUDA_TRY(cudaMemsetAsync(sums, 0, (size_t)k * d * sizeof(double), st));
+      DCG_CUDA_TRY(cudaMemsetAsync(counts, 0, (size_t)k * sizeof(double), st));
+    }
   }
   if (dtype_bytes == 4)
     return dispatch_kmeans<float>((const float*)Y, n, d, ld, centers, k, labels, sums, counts, stats,
@@ -382,6 +387,20 @@ extern "C" int dcg_kmeans_update(const double* sums, const double* counts, int k
   kmeans_update_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(sums, counts, k, d, centers, info);
   DCG_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int dcg_kmeans_iterate(const void* Y, int64_t n, int d, int64_t ld, int dtype_bytes,
+                                  double* centers, int k, int32_t* labels, double* work,
+                                  void* ws, size_t ws_bytes, void* stream) {
+  if (!work) return DCG_E_NULL;
+  double* sums = work;
+  double* counts = work + (size_t)k * d;
+  double* stats = counts + k;
+  double* info = stats + 3;
+  const int rc = dcg_kmeans_step(Y, n, d, ld, dtype_bytes, centers, k, labels, sums, counts, stats, nullptr,
+                                 1, ws, ws_bytes, stream);
+  if (rc) return rc;
+  return dcg_kmeans_update(sums, counts, k, d, centers, info, stream);
 }
 
 extern "C" size_t dcg_nearest_workspace_bytes(int64_t n, int d, int k) {

@@ -106,18 +106,24 @@ def kmeans_lloyd(Y: torch.Tensor, init_centers: torch.Tensor, max_iter: int = 30
     strict = False
     n_iter = 0
     res = None
+    C = C.contiguous()
+    work = ops.kmeans_work(k, d, dev) if shards is None else None
     for it in range(max_iter):
-        res = ops.kmeans_step(Yc, C, labels, update_sums=True, want_gap=False)
-        sums, counts, stats = res["sums"], res["counts"], res["stats"]
-        if shards is not None:
-            packed = shards.allreduce_sum_(torch.cat([sums.reshape(-1), counts, stats]))
+        if shards is None:
+            # single device: memset + E-step + FP64 sums + M-step finish in one library call
+            res = ops.kmeans_iterate_(Yc, C, labels, work)
+            sums, counts = res["sums"], res["counts"]
+            changed, _, _, n_empty, shift_tot = work[k * d + k:k * d + k + 5].tolist()   # ONE host read
+        else:
+            res = ops.kmeans_step(Yc, C, labels, update_sums=True, want_gap=False)
+            packed = shards.allreduce_sum_(torch.cat([res["sums"].reshape(-1), res["counts"], res["stats"]]))
             sums = packed[:k * d].view(k, d)
             counts = packed[k * d:k * d + k]
             stats = packed[k * d + k:]
-        # M-step finish on the device (centres updated in place unless a cluster is empty);
-        # ONE host read per iteration: [n_empty, shift, changed]
-        info = ops.kmeans_update_(C, sums.contiguous(), counts.contiguous())
-        n_empty, shift_tot, changed = torch.cat([info, stats[:1]]).tolist()
+            # M-step finish on the device (centres updated in place unless a cluster is empty);
+            # ONE host read per iteration: [n_empty, shift, changed]
+            info = ops.kmeans_update_(C, sums.contiguous(), counts.contiguous())
+            n_empty, shift_tot, changed = torch.cat([info, stats[:1]]).tolist()
         if n_empty > 0:
             empty = torch.nonzero(counts == 0).flatten()
             sums, counts = _relocate_empty(Yc, C, labels, sums, counts, empty, shards)

@@ -267,6 +267,38 @@ def kmeans_update_(centers: torch.Tensor, sums: torch.Tensor, counts: torch.Tens
     return info
 
 
+def kmeans_work(k: int, d: int, device) -> torch.Tensor:
+    """Work buffer of ``kmeans_iterate_``: [sums k*d | counts k | stats 3 | info 2] FP64."""
+    return torch.empty(k * d + k + 5, dtype=torch.float64, device=device)
+
+
+def kmeans_iterate_(Y: torch.Tensor, centers: torch.Tensor, labels: torch.Tensor,
+                    work: torch.Tensor) -> dict:
+    """One whole Lloyd iteration on one device in ONE library call (memset, E-step + FP64 sums,
+    M-step finish): ``centers`` (k x d FP64) and ``labels`` are updated in place.  Returns views
+    into ``work``: sums, counts, stats [changed, inertia, ties], info [n_empty, shift]."""
+    _need_cuda("Y", Y)
+    _need_cuda("centers", centers, torch.float64)
+    _need_cuda("labels", labels, torch.int32)
+    _need_cuda("work", work, torch.float64)
+    n, d, ld = _rows("Y", Y)
+    k = centers.shape[0]
+    if not centers.is_contiguous() or centers.shape[1] != d or work.numel() < k * d + k + 5:
+        raise ValueError("centers must be contiguous (k, d) and work at least k*d + k + 5 doubles")
+    ws = _KM_WS.get(Y.device)
+    if ws is None:
+        ws = _KM_WS[Y.device] = _ws(256, Y.device)
+    _lib.call("dcg_kmeans_iterate", Y.data_ptr(), n, d, ld, _dtype_bytes(Y), centers.data_ptr(), k,
+              labels.data_ptr(), work.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+    _count(2)
+    o = k * d
+    return {"sums": work[:o].view(k, d), "counts": work[o:o + k], "stats": work[o + k:o + k + 3],
+            "info": work[o + k + 3:o + k + 5]}
+
+
+_KM_WS = {}
+
+
 def nearest_to_centers(Y: torch.Tensor, centers: torch.Tensor) -> torch.Tensor:
     """Index of the first arg-min sample per centre (reference statistics.py:370-377)."""
     _need_cuda("Y", Y)

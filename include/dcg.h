@@ -123,6 +123,15 @@ int dcg_kmeans_step(const void* Y, int64_t n, int d, int64_t ld, int dtype_bytes
 int dcg_kmeans_update(const double* sums, const double* counts, int k, int d,
                       double* centers, double* info, void* stream);
 
+/* ---- K1: one whole Lloyd iteration on one device ----------------------------------------------
+ * dcg_kmeans_step (E-step + FP64 sums) followed by dcg_kmeans_update (M-step finish) in one call.
+ * `work` holds k*d + k + 5 doubles: [sums k*d | counts k | stats 3 | info 2] (overwritten); see the
+ * two entry points above for their meaning.  `centers` is updated in place unless a cluster came
+ * out empty (info[0] > 0).  Sharded runs call the two halves around their all-reduce instead.   */
+int dcg_kmeans_iterate(const void* Y, int64_t n, int d, int64_t ld, int dtype_bytes,
+                       double* centers, int k, int32_t* labels, double* work,
+                       void* ws, size_t ws_bytes, void* stream);
+
 /* ---- K3: nearest sample to each centre -------------------------------------------------------
  * Replaces `statistics.find_centroids` (statistics.py:370-377): argmin_t ||y_t - c_j||_2 per
  * centre j, first index on ties, evaluated in FP64.  argmin is int64[k].                        */

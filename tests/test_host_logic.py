@@ -323,8 +323,22 @@ def test_lloyd_driver_control_flow_with_emulated_kernel(monkeypatch, kmeans_ref)
             C.copy_(C_new)
         return torch.tensor([float(n_empty), shift], dtype=torch.float64)
 
+    def fake_iterate(Y, C, labels, work):
+        # dcg_kmeans_iterate: work = [sums | counts | stats 3 | info 2]
+        k, d = C.shape
+        r = fake_step(Y, C, labels)
+        info = fake_update(C, r["sums"], r["counts"])
+        work[:k * d] = r["sums"].reshape(-1)
+        work[k * d:k * d + k] = r["counts"]
+        work[k * d + k:k * d + k + 3] = r["stats"]
+        work[k * d + k + 3:k * d + k + 5] = info
+        return {"sums": work[:k * d].view(k, d), "counts": work[k * d:k * d + k],
+                "stats": work[k * d + k:k * d + k + 3], "info": work[k * d + k + 3:k * d + k + 5]}
+
     monkeypatch.setattr(ops, "kmeans_step", fake_step)
     monkeypatch.setattr(ops, "kmeans_update_", fake_update)
+    monkeypatch.setattr(ops, "kmeans_iterate_", fake_iterate)
+    monkeypatch.setattr(ops, "kmeans_work", lambda k, d, device: torch.zeros(k * d + k + 5, dtype=torch.float64))
     for name in ("blobs_d2_k5", "blobs_d4_k10_grid", "uniform_d3_k7_grid"):
         X = torch.from_numpy(kmeans_ref[f"{name}_X"])
         res = statistics.kmeans_lloyd(X, torch.from_numpy(kmeans_ref[f"{name}_init"]))
