@@ -30,57 +30,6 @@ EIG_STATS = {"fast": 0, "dense": 0, "last_iters": 0}
 
 # Below this size the dense path is as fast as the iteration.
 _PARTIAL_MIN_F = 192
-_ROUND_ITERS = 4
-
-
-class _InverseIterationRound:
-    """`_ROUND_ITERS` steps X <- K^-1 B X (GEMM-only solves with one refinement step) on static
-    buffers, captured once per (batch, F, b, device) in a CUDA graph: the ~30 skinny kernels of a
-    round take 10-20 us each, less than the CPU needs to launch them (the eigen stage was
-    launch-bound: 5 ms of CPU per 2.7 ms of GPU work at F = 1000).  On CPU tensors (host-logic
-    tests) the same arithmetic runs eagerly."""
-    _cache = {}
-
-    @classmethod
-    def get(cls, nb, F, b, device, dtype):
-        key = (nb, F, b, str(device), dtype)
-        if key not in cls._cache:
-            cls._cache[key] = cls(nb, F, b, device, dtype)
-        return cls._cache[key]
-
-    def __init__(self, nb, F, b, device, dtype):
-        self.B = torch.zeros((nb, F, F), dtype=dtype, device=device)
-        self.K = torch.zeros((nb, F, F), dtype=dtype, device=device)
-        self.Li = torch.zeros((nb, F, F), dtype=dtype, device=device)
-        self.X = torch.ones((nb, F, b), dtype=dtype, device=device)
-        self.out = None
-        self.graph = None
-        if device.type == "cuda":
-            side = torch.cuda.Stream(device)
-            side.wait_stream(torch.cuda.current_stream(device))
-            with torch.cuda.stream(side):
-                self._body()                                 # warm-up (cuBLAS handles, workspaces)
-            torch.cuda.current_stream(device).wait_stream(side)
-            self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
-                self.out = self._body()
-
-    def _body(self):
-        X = self.X
-        for _ in range(_ROUND_ITERS):
-            Z = self.B @ X
-            Y = self.Li.mT @ (self.Li @ Z)
-            R = torch.baddbmm(Z, self.K, Y, alpha=-1.0)       # Z - K Y
-            X = torch.baddbmm(Y, self.Li.mT, self.Li @ R)      # one step of iterative refinement
-            X = X / torch.linalg.norm(X, dim=-2, keepdim=True)
-        return X
-
-    def run(self, B, K, Li, X):
-        self.B.copy_(B); self.K.copy_(K); self.Li.copy_(Li); self.X.copy_(X)
-        if self.graph is None:
-            return self._body()
-        self.graph.replay()
-        return self.out
 
 
 def _shift_invert_topk(B: torch.Tensor, Ct: torch.Tensor, out: int, tol: float = 1e-12,
