@@ -185,6 +185,33 @@ def test_cov_unaligned_rows_and_block_origins(dev, f, ld_pad, block):
     _assert_cov_close(s, oracle.lagged_sums(Z, lag), 1e-5, block=block)
 
 
+@pytest.mark.parametrize("engine", ["tc_3xf16", "tc_3xtf32"])
+def test_cov_split_precision_edge_columns(dev, engine):
+    """Columns that stress the split-precision operands: a constant feature (range -> 1, z = 0), a
+    feature with |mean| / std = 1e5, one with std 1e-6, a heavy-tailed one (|z| up to ~20) and
+    exact zeros.  FP16 pieces must stay inside their range and reproduce the float64 sums."""
+    from deep_cartograph_b200 import ops
+    n, f, lag = 6000, 132, 3
+    X = synth_features(n, f, seed=77).astype(np.float64)
+    rng = np.random.default_rng(5)
+    X[:, 3] = 2.5                                              # constant
+    X[:, 10] = 1.0e3 + 1.0e-2 * rng.standard_normal(n)          # |mean| >> std
+    X[:, 20] = 0.7 + 1.0e-6 * rng.standard_normal(n)            # tiny spread
+    t = rng.standard_t(2.2, size=n)
+    X[:, 30] = np.clip(t, -200, 200)                            # heavy tails
+    X[:, 40] = 0.0
+    X[::2, 41] = 0.0                                            # half zeros
+    X = X.astype(np.float32)
+    st = oracle.column_stats(X)
+    m, r = oracle.prepare_normalization(st, "mean_std")
+    Z = oracle.standardize(X, m, r)
+    assert np.abs(Z).max() > 15                                 # the heavy-tailed column really is
+    s = ops.lagged_covariance(_cuda(X, dev), lag, _cuda(m.astype(np.float32), dev),
+                              _cuda(r.astype(np.float32), dev), engine=engine)
+    _assert_cov_close(s, oracle.lagged_sums(Z, lag), 1e-5)
+    assert torch.isfinite(s["S0"]).all() and torch.isfinite(s["St"]).all()
+
+
 def test_cov_full_size_c2_properties(dev):
     """BASELINE config C2 (1M frames x 1000 features, lag 10) through size-independent properties:
     (i) linearity -- the sums over the whole series equal the sums over two shards with a lag halo
