@@ -28,3 +28,47 @@ extern "C" int dcg_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   if (cc_minor) *cc_minor = p.minor;
   return 0;
 }
+
+// ---- per-device, per-kernel attribute caches (see dcg_common.cuh) --------------------------------
+#include <mutex>
+namespace dcg {
+namespace {
+struct FuncEntry { const void* func; int device; size_t smem_set; int occ_threads; size_t occ_smem; int occ; };
+constexpr int kMaxFuncEntries = 512;
+FuncEntry g_funcs[kMaxFuncEntries];
+int g_n_funcs = 0;
+std::mutex g_funcs_mutex;
+
+FuncEntry* find_entry(const void* func, int device) {
+  for (int i = 0; i < g_n_funcs; ++i)
+    if (g_funcs[i].func == func && g_funcs[i].device == device) return &g_funcs[i];
+  if (g_n_funcs == kMaxFuncEntries) return nullptr;
+  g_funcs[g_n_funcs] = FuncEntry{func, device, 0, 0, 0, 0};
+  return &g_funcs[g_n_funcs++];
+}
+}  // namespace
+
+cudaError_t ensure_dynamic_smem(const void* func, size_t bytes) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(g_funcs_mutex);
+  FuncEntry* en = find_entry(func, dev);
+  if (en && en->smem_set >= bytes && en->smem_set > 0) return cudaSuccess;
+  e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess && en) en->smem_set = bytes;
+  return e;
+}
+
+cudaError_t cached_occupancy(int* per_sm, const void* func, int threads, size_t smem) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(g_funcs_mutex);
+  FuncEntry* en = find_entry(func, dev);
+  if (en && en->occ > 0 && en->occ_threads == threads && en->occ_smem == smem) { *per_sm = en->occ; return cudaSuccess; }
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, func, threads, smem);
+  if (e == cudaSuccess && en) { en->occ = *per_sm; en->occ_threads = threads; en->occ_smem = smem; }
+  return e;
+}
+}  // namespace dcg

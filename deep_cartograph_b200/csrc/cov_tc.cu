@@ -518,7 +518,7 @@ int env_int(const char* name, int dflt) {
 template <int PREC, int VEC>
 int launch_variant(const Params& p, int64_t n_items, cudaStream_t st) {
   auto kern = cov_tc_kernel<PREC, VEC>;
-  DCG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  DCG_CUDA_TRY(ensure_dynamic_smem((const void*)kern, (size_t)(kSmemBytes)));
   const int n_clusters = (int)std::min<int64_t>(kNumSMs / 2, n_items);
   kern<<<2 * n_clusters, kThreads, kSmemBytes, st>>>(p);
   DCG_LAUNCH_CHECK();

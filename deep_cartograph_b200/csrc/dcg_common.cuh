@@ -22,6 +22,14 @@ namespace dcg {
 
 constexpr int kNumSMs = 148;  // B200
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) costs ~100 us of host time per call (measured:
+// it was the whole cost of the small kernels that called it on every launch), so it is issued only
+// when the requested size exceeds what this kernel already has on this device.  The table is the
+// library's only mutable global state (a lazily filled per-device, per-kernel cache).
+cudaError_t ensure_dynamic_smem(const void* func, size_t bytes);
+// cached cudaOccupancyMaxActiveBlocksPerMultiprocessor (same reason)
+cudaError_t cached_occupancy(int* per_sm, const void* func, int threads, size_t smem);
+
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 

@@ -321,9 +321,9 @@ static int launch_kmeans(const T* Y, int64_t n, int d, int64_t ld, const double*
   const KmSmemPlan plan = km_plan(d, DP, k);
   if (plan.total > kKmSmemBudget) return DCG_E_SHAPE;
   auto kern = kmeans_step_kernel<T, DP>;
-  DCG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.total));
+  DCG_CUDA_TRY(ensure_dynamic_smem((const void*)kern, (size_t)(plan.total)));
   int per_sm = 1;
-  DCG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kKmThreads, plan.total));
+  DCG_CUDA_TRY(cached_occupancy(&per_sm, (const void*)kern, kKmThreads, plan.total));
   if (per_sm < 1) per_sm = 1;
   const int64_t ntiles = ceil_div(n, kKmThreads * km_frames_per_thread(DP));
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, (int64_t)kNumSMs * per_sm));
@@ -425,10 +425,10 @@ extern "C" int dcg_nearest_to_centers(const void* Y, int64_t n, int d, int64_t l
   dim3 grid((unsigned)ceil_div(k, kNcThreads), (unsigned)tiles);
   const size_t smem = (size_t)tr * d * sizeof(double);
   if (dtype_bytes == 4) {
-    DCG_CUDA_TRY(cudaFuncSetAttribute(nearest_partial_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DCG_CUDA_TRY(ensure_dynamic_smem((const void*)nearest_partial_kernel<float>, (size_t)(smem)));
     nearest_partial_kernel<float><<<grid, kNcThreads, smem, st>>>((const float*)Y, n, d, ld, tr, centers, k, pdist, pidx);
   } else {
-    DCG_CUDA_TRY(cudaFuncSetAttribute(nearest_partial_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DCG_CUDA_TRY(ensure_dynamic_smem((const void*)nearest_partial_kernel<double>, (size_t)(smem)));
     nearest_partial_kernel<double><<<grid, kNcThreads, smem, st>>>((const double*)Y, n, d, ld, tr, centers, k, pdist, pidx);
   }
   DCG_LAUNCH_CHECK();

@@ -8,10 +8,12 @@ namespace dcg {
 
 // out layout (doubles): [0]=sum w, [1]=sum wl, [2..2+d)=sum w f, then d*d sum w f f^T,
 // d*d sum wl f g^T, d sum wl f, d sum wl g.
-// One warp handles a strip of rows; lane pair (i, j) ownership: lane l accumulates entries
-// e = l, l+32, ... of the d*d matrices in FP32 over <= 64 rows, then FP64.
+// A CTA stages kTcRowsPerCta rows (f row, g row, w, wl) in shared memory; thread e < d*d owns the
+// matrix entry (i, j) = (e / d, e % d) of BOTH matrices, thread d*d + i the three vector entries of
+// component i, thread d*d + d the two weight sums -- uniform code inside each class, rows unrolled
+// by 4, FP32 within the CTA's rows, FP64 across CTAs (one atomic per entry and CTA).
 constexpr int kTcThreads = 256;
-constexpr int kTcRowsPerCta = 512;
+constexpr int kTcRowsPerCta = 128;
 
 __global__ void __launch_bounds__(kTcThreads)
 ticacov_kernel(const float* __restrict__ f, const float* __restrict__ g, const float* __restrict__ w,
@@ -30,39 +32,44 @@ ticacov_kernel(const float* __restrict__ f, const float* __restrict__ g, const f
     sm[r * stride + 2 * d + 1] = wl ? wl[r0 + r] : 1.f;
   }
   __syncthreads();
-  const int n_out = 2 + d + 2 * d * d + 2 * d;
-  for (int e = threadIdx.x; e < n_out; e += kTcThreads) {
-    double acc = 0.0;
-    // decode entry
-    int kind, i = 0, j = 0;
-    if (e == 0) kind = 0;
-    else if (e == 1) kind = 1;
-    else if (e < 2 + d) { kind = 2; i = e - 2; }
-    else if (e < 2 + d + d * d) { kind = 3; i = (e - 2 - d) / d; j = (e - 2 - d) % d; }
-    else if (e < 2 + d + 2 * d * d) { kind = 4; i = (e - 2 - d - d * d) / d; j = (e - 2 - d - d * d) % d; }
-    else if (e < 2 + 2 * d + 2 * d * d) { kind = 5; i = e - (2 + d + 2 * d * d); }
-    else { kind = 6; i = e - (2 + 2 * d + 2 * d * d); }
-    for (int rb = 0; rb < rows; rb += 64) {
-      float p = 0.f;
-      const int re = min(rows, rb + 64);
-      for (int r = rb; r < re; ++r) {
+  const int dd = d * d;
+  double* o_swf = out + 2;
+  double* o_sff = out + 2 + d;
+  double* o_sfg = o_sff + dd;
+  double* o_slf = o_sfg + dd;
+  double* o_slg = o_slf + d;
+  for (int e = threadIdx.x; e < dd + d + 1; e += kTcThreads) {
+    if (e < dd) {
+      const int i = e / d, j = e - i * d;
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll 4
+      for (int r = 0; r < rows; ++r) {
         const float* row = sm + r * stride;
-        const float ww = row[2 * d], wwl = row[2 * d + 1];
-        float v;
-        switch (kind) {
-          case 0: v = ww; break;
-          case 1: v = wwl; break;
-          case 2: v = ww * row[i]; break;
-          case 3: v = ww * row[i] * row[j]; break;
-          case 4: v = wwl * row[i] * row[d + j]; break;
-          case 5: v = wwl * row[i]; break;
-          default: v = wwl * row[d + i]; break;
-        }
-        p += v;
+        const float fi = row[i];
+        a0 = fmaf(row[2 * d] * fi, row[j], a0);
+        a1 = fmaf(row[2 * d + 1] * fi, row[d + j], a1);
       }
-      acc += (double)p;
+      atomicAdd(o_sff + e, (double)a0);
+      atomicAdd(o_sfg + e, (double)a1);
+    } else if (e < dd + d) {
+      const int i = e - dd;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll 4
+      for (int r = 0; r < rows; ++r) {
+        const float* row = sm + r * stride;
+        a0 = fmaf(row[2 * d], row[i], a0);
+        a1 = fmaf(row[2 * d + 1], row[i], a1);
+        a2 = fmaf(row[2 * d + 1], row[d + i], a2);
+      }
+      atomicAdd(o_swf + i, (double)a0);
+      atomicAdd(o_slf + i, (double)a1);
+      atomicAdd(o_slg + i, (double)a2);
+    } else {
+      float a0 = 0.f, a1 = 0.f;
+      for (int r = 0; r < rows; ++r) { a0 += sm[r * stride + 2 * d]; a1 += sm[r * stride + 2 * d + 1]; }
+      atomicAdd(out + 0, (double)a0);
+      atomicAdd(out + 1, (double)a1);
     }
-    atomicAdd(out + e, acc);
   }
 }
 
@@ -82,7 +89,7 @@ extern "C" int dcg_ticacov_f32(const float* f, const float* g, const float* w, c
   cudaStream_t st = (cudaStream_t)stream;
   DCG_CUDA_TRY(cudaMemsetAsync(out, 0, dcg_ticacov_out_doubles(d) * sizeof(double), st));
   const size_t smem = (size_t)kTcRowsPerCta * (2 * d + 2) * sizeof(float);
-  DCG_CUDA_TRY(cudaFuncSetAttribute(ticacov_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  DCG_CUDA_TRY(ensure_dynamic_smem((const void*)ticacov_kernel, (size_t)(smem)));
   ticacov_kernel<<<(unsigned)ceil_div(B, kTcRowsPerCta), kTcThreads, smem, st>>>(f, g, w, wl, B, d, out);
   DCG_LAUNCH_CHECK();
   return 0;
