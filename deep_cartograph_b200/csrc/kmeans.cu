@@ -178,20 +178,39 @@ kmeans_step_kernel(const T* __restrict__ Y, int64_t n, int d, int64_t ld,
         km_refine_warp(s_yy[tid >> 5], d, centers, k, rl, rb, rs);
         if (lane == src) { l = rl; b = rb; s2 = rs; }
       }
-      if (!live) continue;
-      const double g = s2 - b;
-      if (k > 1 && g <= 0.0) ++t_ties;
-      if (gap) gap[idx[r]] = (T)g;
-      if (labels[idx[r]] != l) { ++t_changed; labels[idx[r]] = l; }
-      t_inertia += fmax(b + (double)xsq[r], 0.0);
+      if (live) {
+        const double g = s2 - b;
+        if (k > 1 && g <= 0.0) ++t_ties;
+        if (gap) gap[idx[r]] = (T)g;
+        if (labels[idx[r]] != l) { ++t_changed; labels[idx[r]] = l; }
+        t_inertia += fmax(b + (double)xsq[r], 0.0);
+      }
       if (update_sums) {
+        // Frames of a trajectory are time-ordered, so the 32 frames of a warp usually share one
+        // label: then the warp reduces each coordinate by shuffles (FP64) and one lane adds once --
+        // per-lane FP64 shared-memory atomics are CAS loops that would retry up to 32 times on the
+        // same word.  Mixed warps fall back to per-lane adds.
+        int same = 0;
+        __match_all_sync(0xffffffffu, live ? l : (-1 - (tid & 31)), &same);
         double* a = plan.smem_acc ? (acc_w + (size_t)l * (d + 1)) : nullptr;
-        if (a) {
-          for (int q = 0; q < d; ++q) atomicAdd(a + q, (double)yrow[q]);
-          atomicAdd(a + d, 1.0);
-        } else {
-          for (int q = 0; q < d; ++q) atomicAdd(sums + (size_t)l * d + q, (double)yrow[q]);
-          atomicAdd(counts + l, 1.0);
+        if (same) {
+          for (int q = 0; q < d; ++q) {
+            const double v = warp_sum((double)yrow[q]);
+            if ((tid & 31) == 0) {
+              if (a) atomicAdd(a + q, v); else atomicAdd(sums + (size_t)l * d + q, v);
+            }
+          }
+          if ((tid & 31) == 0) {
+            if (a) atomicAdd(a + d, 32.0); else atomicAdd(counts + l, 32.0);
+          }
+        } else if (live) {
+          if (a) {
+            for (int q = 0; q < d; ++q) atomicAdd(a + q, (double)yrow[q]);
+            atomicAdd(a + d, 1.0);
+          } else {
+            for (int q = 0; q < d; ++q) atomicAdd(sums + (size_t)l * d + q, (double)yrow[q]);
+            atomicAdd(counts + l, 1.0);
+          }
         }
       }
     }
