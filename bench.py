@@ -152,7 +152,9 @@ def run_reference_arm(args):
     # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host thread (set before
     # numpy / torch / sklearn are imported)
     os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
-    steps, warmup = max(1, args.steps), max(0, min(args.warmup, 1))
+    # each step is ~5.5 s of host work on the bounded sample: at most 10 timed steps and one warm-up so
+    # the arm ends within a few minutes whatever --steps / --warmup ask for (the JSON line says what ran)
+    steps, warmup = max(1, min(args.steps, 10)), max(0, min(args.warmup, 1))
     cb, mean_s = time_reference(CPU_SAMPLE_FRAMES, args.features, steps, warmup)
     line = {"impl": "reference", "metric": "frames/s, TICA C0/Ctau + projection + KMeans (hot path)",
             "value": cb["value"], "unit": "frames/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
