@@ -195,6 +195,29 @@ def test_partial_eigensolver_falls_back_on_flat_spectrum():
     np.testing.assert_allclose(evals.numpy(), ref, rtol=1e-9, atol=1e-12)
 
 
+def test_restandardize_sums_is_exact_algebra():
+    """Sums accumulated under provisional standardisation (m0, r0) map to the sums under the final
+    (mean, range) by the FP64 affine correction the streamed loader relies on."""
+    from deep_cartograph_b200 import linalg
+    g = np.random.default_rng(4)
+    n, f, lag = 500, 7, 3
+    X = g.standard_normal((n, f)) * g.uniform(0.1, 2.0, f) + g.uniform(-3, 3, f)
+    m0, r0 = X[::7].mean(0) + 0.1, X[::7].std(0) * 1.3
+    mean, rng = X.mean(0), X.std(0, ddof=1)
+
+    def sums(m, r):
+        Z = (X - m) / r
+        S0, St, a, b, M = oracle.lagged_sums(Z, lag)
+        t = torch.from_numpy
+        return {"S0": t(S0), "St": t(St), "a": t(a), "b": t(b), "M": M}
+
+    t = torch.from_numpy
+    got = linalg.restandardize_sums(sums(m0, r0), t(m0), t(r0), t(mean), t(rng))
+    ref = sums(mean, rng)
+    for k in ("S0", "St", "a", "b"):
+        np.testing.assert_allclose(got[k].numpy(), ref[k].numpy(), rtol=1e-10, atol=1e-9)
+
+
 def test_tica_failure_raises_for_calculator_to_catch():
     from deep_cartograph_b200 import linalg
     S0 = -torch.eye(3, dtype=torch.float64)
