@@ -224,18 +224,17 @@ __device__ __forceinline__ void mma2_commit_both(uint64_t* bar) {
 }
 
 // 4 consecutive floats of one row with the widest load the row alignment allows
-// (L1::no_allocate: a row segment is used once per SM -- other tiles re-read it from L2)
 template <int VEC>
 __device__ __forceinline__ void load_row4(const float* p, float* x) {
   if (VEC == 4) {
-    const float4 v = ldg_stream4(p);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p));
     x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
   } else if (VEC == 2) {
-    const float2 a = ldg_stream2(p);
-    const float2 b = ldg_stream2(p + 2);
+    const float2 a = __ldg(reinterpret_cast<const float2*>(p));
+    const float2 b = __ldg(reinterpret_cast<const float2*>(p + 2));
     x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y;
   } else {
-    x[0] = ldg_stream1(p); x[1] = ldg_stream1(p + 1); x[2] = ldg_stream1(p + 2); x[3] = ldg_stream1(p + 3);
+    x[0] = __ldg(p); x[1] = __ldg(p + 1); x[2] = __ldg(p + 2); x[3] = __ldg(p + 3);
   }
 }
 
