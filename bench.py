@@ -313,9 +313,10 @@ def main():
     cov_s = float(cov_ms.item()) * 1e-3
     achieved = alg_flops / cov_s / 1e12
     issued_mult = {"tc_3xf16": 3.0, "tc_3xtf32": 3.0, "tc_1xtf32": 1.0, "simt_f32": 1.0}[engine]
-    # DRAM bytes per launch of this kernel at this shape, from the committed ncu --set full capture
-    # (profiles/r1_cov_tc_v2_ncu_summary.txt: dram__bytes_read.sum + dram__bytes_write.sum)
-    traffic = 9.95e9 if (engine in ("tc_3xtf32", "tc_3xf16") and n == N_PER_GPU and f == F) else None
+    # DRAM bytes per launch of this kernel at this shape, from the committed ncu --set full captures
+    # (dram__bytes_read.sum + dram__bytes_write.sum)
+    # (profiles/r1_cov_tc_f16x3_ncu_summary.txt / r1_cov_tc_v2_ncu_summary.txt)
+    traffic = {"tc_3xf16": 11.88e9, "tc_3xtf32": 9.95e9}.get(engine) if (n == N_PER_GPU and f == F) else None
     roofline = {"bound": "tensor", "kernel": f"cov_lag ({engine})", "achieved": achieved, "peak": tf32_peak,
                 "unit": "TFLOP/s", "frac": achieved / tf32_peak, "traffic": traffic,
                 "traffic_note": "bytes/launch (ncu); algorithmic bytes/launch = 4*F*n = %.3g" % (4.0 * f * n),
