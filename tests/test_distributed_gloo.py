@@ -100,6 +100,79 @@ def test_frame_sharding_world2(n, f, lag):
     assert sorted(r[1] for r in results) == ["ok"] * world, results
 
 
+def _kmeans_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import oracle
+        from deep_cartograph_b200 import ops
+        from deep_cartograph_b200.modules.statistics import statistics
+        from deep_cartograph_b200.parallel import FrameShards, shard_range
+
+        def fake_step(Y, C, labels, update_sums=True, want_gap=False):
+            lab, best, second = oracle.kmeans_assign(Y.numpy(), C.numpy())
+            old = labels.numpy().copy()
+            labels.copy_(torch.from_numpy(lab))
+            k, d = C.shape
+            sums = np.zeros((k, d)); np.add.at(sums, lab, Y.numpy().astype(np.float64))
+            stats = torch.tensor([float((old != lab).sum()), float((best + (Y.numpy() ** 2).sum(1)).sum()),
+                                  float((second - best <= 0).sum())], dtype=torch.float64)
+            return {"sums": torch.from_numpy(sums), "counts": torch.from_numpy(np.bincount(lab, minlength=k).astype(np.float64)),
+                    "stats": stats, "gap": None}
+
+        def fake_update(C, sums, counts, info=None):
+            n_empty = int((counts == 0).sum())
+            shift = 0.0
+            if n_empty == 0:
+                C_new = sums * (1.0 / counts).unsqueeze(1)
+                shift = float(((C_new - C) ** 2).sum())
+                C.copy_(C_new)
+            return torch.tensor([float(n_empty), shift], dtype=torch.float64)
+
+        ops.kmeans_step, ops.kmeans_update_ = fake_step, fake_update
+        g = np.random.default_rng(3)
+        k, d, n = 6, 3, 4001
+        cent = g.uniform(-1, 1, size=(k, d))
+        Y = np.round(cent[g.integers(0, k, size=n)] + 0.15 * g.standard_normal((n, d)), 4)   # CSV hand-off precision
+        init = Y[:k].copy()
+        s, e = shard_range(n, rank, world)
+        res = statistics.kmeans_lloyd(torch.from_numpy(Y[s:e]), torch.from_numpy(init), shards=FrameShards())
+        ref = oracle.kmeans_lloyd(Y, init)
+        assert res["n_iter"] == ref["n_iter"], (res["n_iter"], ref["n_iter"])
+        np.testing.assert_array_equal(res["labels"].numpy(), ref["labels"][s:e])
+        np.testing.assert_allclose(res["centers"].numpy(), ref["centers"], rtol=1e-12, atol=1e-12)
+        out.put((rank, "ok"))
+    except Exception:  # noqa: BLE001
+        import traceback
+        out.put((rank, "FAIL: " + traceback.format_exc()))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_sharded_lloyd_driver_world2():
+    """The Lloyd driver with frames sharded over two ranks (per-iteration all-reduce of
+    [sums | counts | stats], centre update, convergence tests) reproduces the unsharded float64
+    Lloyd: same iteration count, identical labels, same centres.  The device E-step is emulated."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_kmeans_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(240)
+    results = [out.get(timeout=5) for _ in range(world)]
+    for p in procs:
+        assert p.exitcode == 0, results
+    assert sorted(r[1] for r in results) == ["ok"] * world, results
+
+
 def test_shard_range_partitions_all_frames():
     from deep_cartograph_b200.parallel import shard_range
     for n, w in [(10, 3), (1_000_000, 8), (7, 8)]:
