@@ -36,6 +36,9 @@ _SIGNATURES = {
     "dcg_project_workspace_bytes": (_c_sz, [_c_i64, _c_int, _c_int]),
     "dcg_project_f32": (_c_int, [_p, _c_i64, _c_int, _c_i64, _p, _p, _p, _c_int, _p, _p, _p,
                                  _p, _c_sz, _p]),
+    "dcg_project_blocks_workspace_bytes": (_c_sz, [_c_i64, _c_int, _c_int]),
+    "dcg_project_blocks_f32": (_c_int, [_p, _c_i64, _c_int, _c_i64, _p, _p, _p, _c_int, _c_int, _p, _c_i64,
+                                        _p, _c_sz, _p]),
     "dcg_kmeans_workspace_bytes": (_c_sz, [_c_i64, _c_int, _c_int, _c_int]),
     "dcg_kmeans_step": (_c_int, [_p, _c_i64, _c_int, _c_i64, _c_int, _p, _c_int, _p,
                                  _p, _p, _p, _p, _c_int, _p, _c_sz, _p]),

@@ -7,6 +7,7 @@
 // the (padded) weight rows through L1 (W is small and hot).  No shared-memory staging: every
 // X byte is used exactly once.
 #include "dcg_common.cuh"
+#include "project_mma.cuh"
 
 namespace dcg {
 
@@ -207,10 +208,127 @@ static void launch_project(int dp4, dim3 grid, cudaStream_t st, const float* X, 
 
 using namespace dcg;
 
-extern "C" size_t dcg_project_workspace_bytes(int64_t n, int f, int d) {
-  if (n <= 0 || f <= 0 || d <= 0) return 0;
+// ---- streamed tensor-core path (project_mma.cuh) ---------------------------------------------
+namespace {
+
+constexpr int kCombineGrid = 2 * kNumSMs;
+constexpr size_t kPartBudget = (size_t)256 << 20;      // bytes of partial projections per row batch
+
+struct PmPlan {
+  int nr, rw;                 // ranges of the feature axis
+  int64_t batch_rows;         // rows per launch (several ranges only: bounds the partial buffer)
+  int64_t nbatches;
+  size_t bf_bytes, mf_bytes, part_bytes, mm_slots;
+};
+
+static PmPlan pm_plan_dense(int64_t n, int f) {
+  PmPlan p;
+  p.nr = (int)ceil_div(f, pm::kRangeMax);
+  p.rw = (int)(ceil_div(ceil_div(f, p.nr), 16) * 16);
+  p.bf_bytes = align_up((size_t)p.nr * pm::kWarps * 8 * 32 * 16 * sizeof(float), 256);
+  p.mf_bytes = align_up((size_t)p.nr * pm::kWarps * 8 * 32 * 4 * sizeof(float), 256);
+  if (p.nr == 1) {
+    p.batch_rows = n; p.nbatches = 1; p.part_bytes = 0; p.mm_slots = kNumSMs;
+  } else {
+    const int64_t cap = std::max<int64_t>(16, (int64_t)(kPartBudget / ((size_t)p.nr * 16 * sizeof(float))) / 16 * 16);
+    p.batch_rows = std::min<int64_t>(n, cap);
+    p.nbatches = ceil_div(n, p.batch_rows);
+    p.part_bytes = align_up((size_t)p.nr * p.batch_rows * 16 * sizeof(float), 256);
+    p.mm_slots = (size_t)p.nbatches * kCombineGrid;
+  }
+  return p;
+}
+
+static size_t pm_dense_bytes(int64_t n, int f, int d) {
+  const PmPlan p = pm_plan_dense(n, f);
+  return p.bf_bytes + p.mf_bytes + p.part_bytes + 2 * align_up(p.mm_slots * (size_t)d * sizeof(float), 256);
+}
+
+static bool pm_usable(const void* X, int64_t ld) { return ((uintptr_t)X % 16 == 0) && (ld % 4 == 0); }
+
+// rows per work item: single range -> fine-grained (no operand reload between items); several
+// ranges -> coarse enough that reloading the B fragments (<= 150 KB per CTA from L2) is noise
+static int pm_rows_per_item(int nr) { return nr == 1 ? 64 : 512; }
+
+template <int NT>
+static cudaError_t pm_launch(int grid, cudaStream_t st, const float* X, int64_t n, int64_t ld, const pm::Geom& g,
+                             const float* Bf, const float* Mf, float* out, int64_t out_rs, int64_t out_cs,
+                             float* pmn, float* pmx, int mm_ld) {
+  cudaError_t e = ensure_dynamic_smem((const void*)pm::project_mma_kernel<NT>, pm::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  pm::project_mma_kernel<NT><<<grid, pm::kThreads, pm::kSmemBytes, st>>>(
+      X, n, ld, g, pm_rows_per_item(g.nr), reinterpret_cast<const float4*>(Bf), reinterpret_cast<const float4*>(Mf),
+      out, out_rs, out_cs, pmn, pmx, mm_ld);
+  return cudaPeekAtLastError();
+}
+
+static cudaError_t pm_launch_any(int nt, int grid, cudaStream_t st, const float* X, int64_t n, int64_t ld,
+                                 const pm::Geom& g, const float* Bf, const float* Mf, float* out, int64_t out_rs,
+                                 int64_t out_cs, float* pmn, float* pmx, int mm_ld) {
+  return nt == 1 ? pm_launch<1>(grid, st, X, n, ld, g, Bf, Mf, out, out_rs, out_cs, pmn, pmx, mm_ld)
+                 : pm_launch<2>(grid, st, X, n, ld, g, Bf, Mf, out, out_rs, out_cs, pmn, pmx, mm_ld);
+}
+
+static int pm_grid(int64_t n, const pm::Geom& g) {
+  const int64_t items = ceil_div(n, pm_rows_per_item(g.nr)) * g.nr;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(items, kNumSMs));
+}
+
+// dense projection through the streamed path; `w` points at pm_dense_bytes() of workspace
+static int pm_project_dense(const float* X, int64_t n, int f, int64_t ld, const float* mean, const float* range,
+                            const float* W, int d, float* P, float* pmin, float* pmax, char* w, cudaStream_t st) {
+  const PmPlan p = pm_plan_dense(n, f);
+  float* Bf = (float*)w; w += p.bf_bytes;
+  float* Mf = (float*)w; w += p.mf_bytes;
+  float* part = (float*)w; w += p.part_bytes;
+  float* pmn = (float*)w; w += align_up(p.mm_slots * (size_t)d * sizeof(float), 256);
+  float* pmx = (float*)w;
+  const bool want_mm = pmin || pmax;
+  int slots = 0;
+  for (int d0 = 0; d0 < d; d0 += 16) {
+    const int dc = std::min(16, d - d0);
+    pm::Geom g{f, p.rw, p.nr, 0, d, d0, dc};
+    const int nthreads = p.nr * pm::kWarps * 8 * 32;
+    pm::prepare_kernel<<<(unsigned)ceil_div(nthreads, 256), 256, 0, st>>>(g, W, mean, range, Bf, Mf);
+    DCG_LAUNCH_CHECK();
+    const int nt = dc <= 8 ? 1 : 2;
+    if (p.nr == 1) {
+      const int grid = pm_grid(n, g);
+      DCG_CUDA_TRY(pm_launch_any(nt, grid, st, X, n, ld, g, Bf, Mf, P + d0, d, 0,
+                                 want_mm ? pmn + d0 : nullptr, want_mm ? pmx + d0 : nullptr, want_mm ? d : 0));
+      slots = grid;
+    } else {
+      for (int64_t b = 0; b < p.nbatches; ++b) {
+        const int64_t r0 = b * p.batch_rows, nb = std::min<int64_t>(p.batch_rows, n - r0);
+        DCG_CUDA_TRY(pm_launch_any(nt, pm_grid(nb, g), st, X + r0 * ld, nb, ld, g, Bf, Mf, part, dc, nb * dc,
+                                   nullptr, nullptr, 0));
+        // unused slots of a short batch must not be read: every batch publishes kCombineGrid slots
+        pm::combine_kernel<<<kCombineGrid, pm::kCombineThreads, 0, st>>>(
+            part, p.nr, nb, dc, nb * dc, P + r0 * d + d0, d,
+            want_mm ? pmn + (size_t)b * kCombineGrid * d + d0 : nullptr,
+            want_mm ? pmx + (size_t)b * kCombineGrid * d + d0 : nullptr, want_mm ? d : 0);
+        DCG_LAUNCH_CHECK();
+      }
+      slots = (int)(p.nbatches * kCombineGrid);
+    }
+  }
+  if (want_mm) {
+    project_minmax_kernel<<<d, 256, 0, st>>>(pmn, pmx, slots, d, pmin, pmax);
+    DCG_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+static size_t legacy_bytes(int64_t n, int f, int d) {
   return align_up((size_t)(f + 3) * 16 * sizeof(float), 256) + align_up((size_t)(f + 3) * 3 * sizeof(float), 256) +
          2 * align_up((size_t)project_grid(n) * d * sizeof(float), 256);
+}
+
+}  // namespace
+
+extern "C" size_t dcg_project_workspace_bytes(int64_t n, int f, int d) {
+  if (n <= 0 || f <= 0 || d <= 0) return 0;
+  return std::max(legacy_bytes(n, f, d), pm_dense_bytes(n, f, d));
 }
 
 extern "C" int dcg_project_f32(const float* X, int64_t n, int f, int64_t ld,
@@ -223,6 +341,9 @@ extern "C" int dcg_project_f32(const float* X, int64_t n, int f, int64_t ld,
   if (!ws || ws_bytes < dcg_project_workspace_bytes(n, f, d)) return DCG_E_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   char* w = (char*)ws;
+  // 16-byte aligned rows (the layout load_training_tensor produces): streamed tensor-core path
+  if (pm_usable(X, ld)) return pm_project_dense(X, n, f, ld, mean, range, W, d, P, pmin, pmax, w, st);
+  // otherwise: register-tile kernel with 8- or 4-byte loads
   float* Wp = (float*)w;
   w += align_up((size_t)(f + 3) * 16 * sizeof(float), 256);
   float* Cp = (float*)w;
@@ -253,5 +374,35 @@ extern "C" int dcg_project_f32(const float* X, int64_t n, int f, int64_t ld,
     project_minmax_kernel<<<d, 256, 0, st>>>(pmn, pmx, grid, d, pmin, pmax);
     DCG_LAUNCH_CHECK();
   }
+  return 0;
+}
+
+// hTICA level 1: all diagonal blocks projected in one pass over X.
+extern "C" size_t dcg_project_blocks_workspace_bytes(int64_t n, int f, int block) {
+  if (n <= 0 || f <= 0 || block <= 0) return 0;
+  const size_t nr = (size_t)ceil_div(f, block);
+  return align_up(nr * pm::kWarps * 8 * 32 * 16 * sizeof(float), 256) + align_up(nr * pm::kWarps * 8 * 32 * 4 * sizeof(float), 256);
+}
+
+extern "C" int dcg_project_blocks_f32(const float* X, int64_t n, int f, int64_t ld,
+                                      const float* mean, const float* range,
+                                      const float* W, int block, int s, float* P, int64_t p_ld,
+                                      void* ws, size_t ws_bytes, void* stream) {
+  if (!X || !W || !P) return DCG_E_NULL;
+  if ((mean == nullptr) != (range == nullptr)) return DCG_E_NULL;
+  if (n <= 0 || f <= 0 || ld < f || block < 1 || block > pm::kRangeMax - 6 || s < 1 || s > 16) return DCG_E_SHAPE;
+  const int nr = (int)ceil_div(f, block);
+  if (p_ld < (int64_t)(nr - 1) * s + std::min(s, f - (nr - 1) * block)) return DCG_E_SHAPE;
+  if (!pm_usable(X, ld)) return DCG_E_ALIGN;
+  if (!ws || ws_bytes < dcg_project_blocks_workspace_bytes(n, f, block)) return DCG_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  char* w = (char*)ws;
+  float* Bf = (float*)w;
+  w += align_up((size_t)nr * pm::kWarps * 8 * 32 * 16 * sizeof(float), 256);
+  float* Mf = (float*)w;
+  pm::Geom g{f, block, nr, s, s, 0, s};
+  pm::prepare_kernel<<<(unsigned)ceil_div((int64_t)nr * pm::kWarps * 8 * 32, 256), 256, 0, st>>>(g, W, mean, range, Bf, Mf);
+  DCG_LAUNCH_CHECK();
+  DCG_CUDA_TRY(pm_launch_any(s <= 8 ? 1 : 2, pm_grid(n, g), st, X, n, ld, g, Bf, Mf, P, p_ld, s, nullptr, nullptr, 0));
   return 0;
 }

@@ -644,15 +644,28 @@ class HTICACalculator(LinearCalculator):
         # T1 is block diagonal: block b projects only its own columns of X, so the level-1
         # projections are ONE pass over X in total (each call reads one column block)
         chunks = linalg.htica_chunks(self.num_features, self.num_subspaces)
-        parts = []
-        c = 0
-        for (s0, e0) in chunks:
-            w = min(self.subspaces_dimension, e0 - s0)
-            Pc, _, _ = ops.project(self.training_data[:, s0:e0], T1f[s0:e0, c:c + w].contiguous(),
-                                   mean[s0:e0], rng[s0:e0], minmax=False)
-            parts.append(Pc)
-            c += w
-        P = parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)
+        X = self.training_data
+        width, sdim = chunks[0][1] - chunks[0][0], int(self.subspaces_dimension)
+        if (sdim <= 16 and width <= 1018 and X.data_ptr() % 16 == 0 and X.stride(0) % 4 == 0
+                and X.stride(1) == 1):
+            # compact (F, s) weights: row i = the weights of feature i inside its own block
+            Wc = torch.zeros((self.num_features, sdim), dtype=torch.float32, device=T1f.device)
+            c = 0
+            for (s0, e0) in chunks:
+                w = min(sdim, e0 - s0)
+                Wc[s0:e0, :w] = T1f[s0:e0, c:c + w]
+                c += w
+            P = ops.project_blocks(X, Wc, width, mean, rng)
+        else:
+            parts = []
+            c = 0
+            for (s0, e0) in chunks:
+                w = min(sdim, e0 - s0)
+                Pc, _, _ = ops.project(X[:, s0:e0], T1f[s0:e0, c:c + w].contiguous(),
+                                       mean[s0:e0], rng[s0:e0], minmax=False)
+                parts.append(Pc)
+                c += w
+            P = parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)
         if self.shards is not None:
             P = self.shards.with_halo(P, lag)
         s = ops.lagged_covariance(P, lag, engine=self.backend.get("cov_engine"))

@@ -208,8 +208,47 @@ def project(X: torch.Tensor, W: torch.Tensor, mean: Optional[torch.Tensor] = Non
     ws = _ws(lib.dcg_project_workspace_bytes(n, f, d), dev)
     _lib.call("dcg_project_f32", X.data_ptr(), n, f, ld, _ptr(mean), _ptr(rng), W.data_ptr(), d,
               P.data_ptr(), _ptr(pmin), _ptr(pmax), ws.data_ptr(), ws.numel(), _stream())
-    _count(2 * ((d + 15) // 16) + (1 if minmax else 0))
+    passes, nr = (d + 15) // 16, -(-f // 1024)
+    if nr > 1 and X.data_ptr() % 16 == 0 and ld % 4 == 0:     # several feature ranges: row batches + combine
+        cap = max(16, ((256 << 20) // (nr * 64)) // 16 * 16)
+        _count(passes * (1 + 2 * (-(-n // cap))) + (1 if minmax else 0))
+    else:
+        _count(2 * passes + (1 if minmax else 0))
     return P, pmin, pmax
+
+
+def project_blocks(X: torch.Tensor, W: torch.Tensor, block: int, mean: Optional[torch.Tensor] = None,
+                   rng: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """hTICA level 1 (reference cv_calculator.py:2331-2371): every diagonal feature block of width
+    ``block`` (torch.split semantics) projected onto its own ``s = W.shape[1]`` columns in ONE pass
+    over X.  ``W`` is (f, s): row i holds the weights of feature i inside its block.  Returns
+    P (n, sum of min(s, block width)).  Needs 16-byte aligned rows (DcgError -1003 otherwise)."""
+    _need_cuda("X", X, torch.float32)
+    _need_cuda("W", W, torch.float32)
+    n, f, ld = _rows("X", X)
+    if W.dim() != 2 or W.shape[0] != f:
+        raise ValueError(f"W must be ({f}, s)")
+    s = W.shape[1]
+    nb = -(-f // block)
+    cols = (nb - 1) * s + min(s, f - (nb - 1) * block)
+    if (mean is None) != (rng is None):
+        raise ValueError("mean and range must be given together")
+    if mean is not None:
+        _need_cuda("mean", mean, torch.float32)
+        _need_cuda("range", rng, torch.float32)
+        mean = mean.contiguous()
+        rng = rng.contiguous()
+    lib = _lib.load()
+    dev = X.device
+    W = W.contiguous()
+    P = torch.empty((n, cols), dtype=torch.float32, device=dev)
+    if n == 0:
+        return P
+    ws = _ws(lib.dcg_project_blocks_workspace_bytes(n, f, block), dev)
+    _lib.call("dcg_project_blocks_f32", X.data_ptr(), n, f, ld, _ptr(mean), _ptr(rng), W.data_ptr(), block, s,
+              P.data_ptr(), cols, ws.data_ptr(), ws.numel(), _stream())
+    _count(2)
+    return P
 
 
 # ---- K1 / K3 ----------------------------------------------------------------------------------

@@ -95,6 +95,20 @@ int dcg_project_f32(const float* X, int64_t n, int f, int64_t ld,
                     const float* W, int d, float* P, float* pmin, float* pmax,
                     void* ws, size_t ws_bytes, void* stream);
 
+/* ---- A8: hTICA level-1 projections, all diagonal blocks in one pass ------------------------------
+ * Replaces the per-subspace `data @ V_b` loop of `HTICACalculator.compute_cv`
+ * (cv_calculator.py:2331-2371; the block-diagonal T1 of :2367).  Feature block c covers columns
+ * [c*block, min(f, (c+1)*block)) (torch.split semantics: the last block may be narrower) and
+ * projects only them:  P[t, c*s + j] = sum_i ((x_t[i] - mean[i]) / range[i]) * W[i, j],
+ * i in block c, j < min(s, width of block c).  W is f x s row-major: row i holds the s weights
+ * of feature i within its own block.  P is n x p_ld row-major float32.  Needs 16-byte aligned
+ * rows (X % 16 == 0, ld % 4 == 0; else DCG_E_ALIGN), 1 <= s <= 16, block <= 1018.               */
+size_t dcg_project_blocks_workspace_bytes(int64_t n, int f, int block);
+int dcg_project_blocks_f32(const float* X, int64_t n, int f, int64_t ld,
+                           const float* mean, const float* range,
+                           const float* W, int block, int s, float* P, int64_t p_ld,
+                           void* ws, size_t ws_bytes, void* stream);
+
 /* ---- K1: KMeans E-step + M-step sums ---------------------------------------------------------
  * Replaces one sklearn `lloyd_iter` as triggered by `statistics.kmeans_clustering`
  * (modules/statistics/statistics.py:159-197; sklearn/cluster/_k_means_lloyd.pyx:193-214):

@@ -305,6 +305,79 @@ def test_projection_padded_rows(dev, n, f, d, ld):
     np.testing.assert_array_equal(stt["min"].cpu().numpy(), st["min"])
 
 
+@pytest.mark.parametrize("n,f,d,ld", [(3001, 4950, 10, 4952), (1500, 2050, 12, 2052), (700, 1025, 3, 1028),
+                                      (2100, 3000, 20, 3000), (17, 1030, 8, 1032), (40000, 1200, 5, 1200)])
+def test_projection_several_feature_ranges(dev, n, f, d, ld):
+    """f > 1024: the streamed projection cuts the feature axis into ranges whose partial results are
+    summed in range order by the combine kernel (C3 has f = 4950 -> 5 ranges)."""
+    from deep_cartograph_b200 import ops
+    X = synth_features(n, f, seed=d + f)
+    buf = torch.full((n, ld), float("nan"), dtype=torch.float32, device=dev)
+    buf[:, :f] = torch.from_numpy(X).to(dev)
+    st = oracle.column_stats(X)
+    m, r = oracle.prepare_normalization(st, "mean_std")
+    W = (np.random.default_rng(d).standard_normal((f, d)) / np.sqrt(f)).astype(np.float32)
+    ref = oracle.project(oracle.standardize(X, m, r), W)
+    P, pmin, pmax = ops.project(buf[:, :f], _cuda(W, dev), _cuda(m.astype(np.float32), dev),
+                                _cuda(r.astype(np.float32), dev))
+    got = P.cpu().numpy()
+    assert np.isfinite(got).all()
+    np.testing.assert_allclose(got, ref, atol=1e-4 * max(1.0, np.abs(ref).max()))
+    assert np.array_equal(pmin.cpu().numpy(), got.min(axis=0))
+    assert np.array_equal(pmax.cpu().numpy(), got.max(axis=0))
+    P2, _, _ = ops.project(buf[:, :f], _cuda(W, dev), minmax=False)             # no standardisation
+    ref2 = X.astype(np.float64) @ W.astype(np.float64)
+    np.testing.assert_allclose(P2.cpu().numpy(), ref2, atol=1e-4 * max(1.0, np.abs(ref2).max()))
+
+
+def test_projection_is_deterministic_and_tight(dev):
+    """Split-precision tensor-core projection: run-to-run identical bits, and far inside the 1e-4
+    tolerance (the products carry ~2^-22 relative error, the sums are FP32)."""
+    from deep_cartograph_b200 import ops
+    n, f, d = 20000, 1000, 10
+    X = synth_features(n, f, seed=5)
+    st = oracle.column_stats(X)
+    m, r = oracle.prepare_normalization(st, "mean_std")
+    W = (np.random.default_rng(1).standard_normal((f, d)) / np.sqrt(f)).astype(np.float32)
+    ref = oracle.project(oracle.standardize(X, m, r), W)
+    args = (_cuda(X, dev), _cuda(W, dev), _cuda(m.astype(np.float32), dev), _cuda(r.astype(np.float32), dev))
+    P1, _, _ = ops.project(*args)
+    P2, _, _ = ops.project(*args)
+    assert torch.equal(P1, P2)
+    err = np.abs(P1.cpu().numpy() - ref).max() / max(1.0, np.abs(ref).max())
+    assert err < 5e-6, err
+
+
+@pytest.mark.parametrize("n,f,ns,s,ld", [(3000, 4950, 10, 5, 4952), (1234, 1000, 7, 3, 1000), (517, 54, 3, 2, 56),
+                                         (900, 2000, 2, 16, 2000), (2000, 1001, 10, 5, 1004)])
+def test_block_projection_matches_per_block_float64(dev, n, f, ns, s, ld):
+    """hTICA level 1 (reference cv_calculator.py:2331-2371): all diagonal blocks projected in one
+    pass; block starts are not 16-byte aligned (495 floats), the last block may be narrower."""
+    from deep_cartograph_b200 import ops
+    X = synth_features(n, f, seed=ns + f)
+    buf = torch.full((n, ld), float("nan"), dtype=torch.float32, device=dev)
+    buf[:, :f] = torch.from_numpy(X).to(dev)
+    st = oracle.column_stats(X)
+    m, r = oracle.prepare_normalization(st, "mean_std")
+    Z = oracle.standardize(X, m, r).astype(np.float64)
+    width = f // ns
+    chunks = [(a, min(a + width, f)) for a in range(0, f, width)]
+    g = np.random.default_rng(ns)
+    Wc = np.zeros((f, s), dtype=np.float32)
+    refs = []
+    for (a, b) in chunks:
+        w = min(s, b - a)
+        Wc[a:b, :w] = (g.standard_normal((b - a, w)) / np.sqrt(b - a)).astype(np.float32)
+        refs.append(Z[:, a:b] @ Wc[a:b, :w].astype(np.float64))
+    ref = np.concatenate(refs, axis=1)
+    P = ops.project_blocks(buf[:, :f], _cuda(Wc, dev), width, _cuda(m.astype(np.float32), dev),
+                           _cuda(r.astype(np.float32), dev))
+    got = P.cpu().numpy()
+    assert got.shape == ref.shape
+    assert np.isfinite(got).all()
+    np.testing.assert_allclose(got, ref, atol=1e-4 * max(1.0, np.abs(ref).max()))
+
+
 # ------------------------------------------------------------------------------------------------
 # K1 KMeans
 # ------------------------------------------------------------------------------------------------

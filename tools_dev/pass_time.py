@@ -24,7 +24,8 @@ def timeit(fn, reps):
 if what in ("proj", "stats"):
     n, f, d = (a + [1000000, 1000, 4])[:3] if len(a) >= 3 else (1000000, 1000, 4)
     reps = a[3] if len(a) > 3 else 7
-    X = torch.randn((n, f), device=dev) * 0.3 + 2.0
+    ld = (f + 3) // 4 * 4
+    X = (torch.randn((n, ld), device=dev) * 0.3 + 2.0)[:, :f]
     mean = X.mean(0); rng = X.std(0)
     W = torch.randn((f, d), device=dev) / f ** 0.5
     if what == "proj":
