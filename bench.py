@@ -227,6 +227,9 @@ def main():
                 self.e1.record()
                 pass_ev[self.name].append((self.e0, self.e1))
 
+    # |P| <= 1 after the CV min-max normalisation (+ rounding): bound for the fixed-point KMeans sums
+    p_bound = torch.full((1,), 1.0 + 1e-3, dtype=torch.float64, device=dev)
+
     def step(record=False):
       with _Timed("stats", record):
         st = ops.column_stats(X)
@@ -264,9 +267,9 @@ def main():
         work = ops.kmeans_work(K, DIM, dev)
         for _ in range(KM_ITERS):
             if shards is None:
-                ops.kmeans_iterate_(P, C, labels, work)      # one library call per Lloyd iteration
+                ops.kmeans_iterate_(P, C, labels, work, absmax=p_bound)   # one library call per Lloyd iteration
                 continue
-            r = ops.kmeans_step(P, C, labels)
+            r = ops.kmeans_step(P, C, labels, absmax=p_bound)
             packed = shards.allreduce_sum_(torch.cat([r["sums"].reshape(-1), r["counts"]]))
             ops.kmeans_update_(C, packed[:K * DIM].view(K, DIM), packed[K * DIM:])
       return evals, labels
@@ -339,13 +342,29 @@ def main():
         "eigen": {"ms": pm["eigen"], "bound": "none (F x F FP64 eigenproblem, cuSOLVER)"},
         "projection": {"ms": pm["projection"], "alg_bytes": (4.0 * f + 4.0 * DIM) * n + 8.0 * DIM * n, "bound": "hbm",
                        "note": "4F read + 4d written per frame, + 8d for the in-place CV normalisation"},
-        "kmeans": {"ms": pm["kmeans"], "alg_bytes": KM_ITERS * (4.0 * DIM + 4.0) * n, "bound": "hbm (k small)",
-                   "iters": KM_ITERS},
+        "kmeans": {"ms": pm["kmeans"], "alg_bytes": KM_ITERS * (4.0 * DIM + 4.0) * n, "iters": KM_ITERS},
     }
     for v in passes.values():
         if "alg_bytes" in v:
             v["gbs"] = v["alg_bytes"] / (v["ms"] * 1e-3) / 1e9
             v["frac_hbm"] = v["gbs"] / hbm
+    # KMeans: 2*k*d FLOP against 4*d + 4 bytes per frame and iteration; HBM-bound only
+    # below the FP32 ridge (nominal FMA peak / measured HBM, ~11 FLOP/B, i.e. k <~ 24), FP32-FMA-bound
+    # beyond it.  Report the roof that binds.
+    fp32_peak = 148 * 128 * 2 * (peaks.get("sm_max_mhz") or 1965.0) * 1e6 / 1e12      # TFLOP/s, nominal
+    km = passes["kmeans"]
+    km["alg_flop"] = KM_ITERS * 2.0 * K * DIM * n
+    km["tflops_fp32"] = km["alg_flop"] / (km["ms"] * 1e-3) / 1e12
+    km["intensity_flop_per_byte"] = km["alg_flop"] / km["alg_bytes"]
+    if km["intensity_flop_per_byte"] > fp32_peak * 1e3 / hbm:
+        km["bound"] = "fp32 fma (k*d/(2d+2) FLOP/B above the ridge)"
+        km["frac_fp32"] = km["tflops_fp32"] / fp32_peak
+        km["fp32_peak_nominal"] = fp32_peak
+    else:
+        km["bound"] = "hbm (k small)"
+    km["note"] = ("10 whole Lloyd iterations (memset + E-step + FP64/fixed-point sums + centre update per "
+                  "iteration) on n x d projected frames: at this size (16 MB) the pass is launch- and "
+                  "latency-bound, see profiles/ for the stand-alone E-step at C5 size")
 
     # ---- e2e through the public API with host buffers
     e2e = None

@@ -74,12 +74,22 @@ __device__ __forceinline__ void km_refine_warp(const double* __restrict__ yy_s, 
   }
 }
 
+// slot (8 bytes of shared memory, two's complement in two 32-bit words) += round(v)
+__device__ __forceinline__ void km_add_fixed(double* slot, double v) {
+  const long long iv = __double2ll_rn(v);
+  const unsigned int lo = (unsigned int)iv;
+  unsigned int* w = reinterpret_cast<unsigned int*>(slot);
+  const unsigned int old = atomicAdd(w, lo);
+  const int hi = (int)(iv >> 32) + (((old + lo) < lo) ? 1 : 0);
+  if (hi != 0) atomicAdd(reinterpret_cast<int*>(w + 1), hi);
+}
+
 template <typename T, int DP>
 __global__ void __launch_bounds__(kKmThreads, 1)
 kmeans_step_kernel(const T* __restrict__ Y, int64_t n, int d, int64_t ld,
                    const double* __restrict__ centers, int k, int32_t* __restrict__ labels,
                    double* __restrict__ sums, double* __restrict__ counts, double* __restrict__ stats,
-                   T* __restrict__ gap, int update_sums, KmSmemPlan plan) {
+                   T* __restrict__ gap, int update_sums, const double* __restrict__ y_absmax, KmSmemPlan plan) {
   constexpr int kKmR = km_frames_per_thread(DP);
   constexpr int kKmTile = kKmThreads * kKmR;
   extern __shared__ __align__(16) unsigned char smem[];
@@ -88,8 +98,33 @@ kmeans_step_kernel(const T* __restrict__ Y, int64_t n, int d, int64_t ld,
   double* acc_s = reinterpret_cast<double*>(smem + plan.acc_off);
   __shared__ float s_cmax2;
   __shared__ double s_yy[kKmThreads / 32][32];      // frame broadcast for the cooperative FP64 refine
+  __shared__ double s_scale[2];                     // fixed-point scale 2^s and 2^-s (0: FP64 atomics)
 
   const int tid = threadIdx.x;
+  if (tid == 0) {
+    // Fixed-point M-step sums.  Shared memory has no native 64-bit atomic add (FP64 and u64 both
+    // compile to a CAS loop, which at small k retries ~7 times per add: ncu, 46 % of all stall
+    // samples), but 32-bit integer adds are native.  With a bound |y| <= y_absmax from the caller
+    // every value is added as round(y * 2^s) in two 32-bit words (low word first, its carry goes
+    // to the high word): exact integer arithmetic, independent of the order of the adds.
+    // s is the largest exponent for which the sum over all frames of this CTA fits in 62 bits;
+    // a value is rounded at 2^-s ~ |y|max * frames_per_cta * 2^-61 (<= 2^-44 |y|max for 128 k frames).
+    double sc = 0.0, isc = 0.0;
+    if (y_absmax && update_sums && plan.smem_acc) {
+      const double b = *y_absmax;
+      if (b >= 0.0 && b < 1e300) {
+        const int64_t tiles_cta = (((n + kKmTile - 1) / kKmTile) + gridDim.x - 1) / gridDim.x;
+        const int64_t frames_cta = min(n, tiles_cta * (int64_t)kKmTile);
+        const int e_f = 64 - __clzll((long long)frames_cta);
+        const int e_y = b > 0.0 ? ilogb(b) + 1 : 0;
+        const int e = 62 - e_f - e_y;
+        sc = ldexp(1.0, e);
+        isc = ldexp(1.0, -e);
+      }
+    }
+    s_scale[0] = sc;
+    s_scale[1] = isc;
+  }
   for (int i = tid; i < k * DP; i += kKmThreads) {
     const int j = i / DP, q = i - j * DP;
     c_s[i] = (q < d) ? (float)centers[(size_t)j * d + q] : 0.f;
@@ -106,6 +141,8 @@ kmeans_step_kernel(const T* __restrict__ Y, int64_t n, int d, int64_t ld,
     for (int i = tid; i < plan.smem_acc * k * (d + 1); i += kKmThreads) acc_s[i] = 0.0;
   double* acc_w = acc_s + (size_t)((tid >> 5) % (plan.smem_acc > 0 ? plan.smem_acc : 1)) * k * (d + 1);
   __syncthreads();
+  const double fx_scale = s_scale[0];
+  const bool fixed = fx_scale != 0.0;
   const float cmax2 = s_cmax2 * 1.0001f + 1e-30f;
   const float cmaxn = sqrtf(cmax2);
   // |err(score_a) - err(score_b)| <= 2 u (2d+6) (cmax2 + |y| |c|max), u = 2^-24; x1.5 margin
@@ -119,9 +156,11 @@ kmeans_step_kernel(const T* __restrict__ Y, int64_t n, int d, int64_t ld,
     float x[kKmR][DP];
     int64_t idx[kKmR];
     float xsq[kKmR];
+    int lab_old[kKmR];          // previous labels: loaded with the frames, needed only after the scan
 #pragma unroll
     for (int r = 0; r < kKmR; ++r) {
       idx[r] = tile * kKmTile + (int64_t)r * kKmThreads + tid;
+      lab_old[r] = labels[min(idx[r], n - 1)];
       const T* yrow = Y + min(idx[r], n - 1) * ld;
       xsq[r] = 0.f;
 #pragma unroll
@@ -182,7 +221,7 @@ kmeans_step_kernel(const T* __restrict__ Y, int64_t n, int d, int64_t ld,
         const double g = s2 - b;
         if (k > 1 && g <= 0.0) ++t_ties;
         if (gap) gap[idx[r]] = (T)g;
-        if (labels[idx[r]] != l) { ++t_changed; labels[idx[r]] = l; }
+        if (lab_old[r] != l) { ++t_changed; labels[idx[r]] = l; }
         t_inertia += fmax(b + (double)xsq[r], 0.0);
       }
       if (update_sums) {
@@ -193,18 +232,31 @@ kmeans_step_kernel(const T* __restrict__ Y, int64_t n, int d, int64_t ld,
         int same = 0;
         __match_all_sync(0xffffffffu, live ? l : (-1 - (tid & 31)), &same);
         double* a = plan.smem_acc ? (acc_w + (size_t)l * (d + 1)) : nullptr;
+        // float32 frames are still in registers (x[r][.]); float64 frames are re-read (L1)
+        auto yval = [&](int q) -> double {
+          if constexpr (sizeof(T) == 4) return (double)x[r][q]; else return (double)yrow[q];
+        };
         if (same) {
-          for (int q = 0; q < d; ++q) {
-            const double v = warp_sum((double)yrow[q]);
+#pragma unroll
+          for (int q = 0; q < DP; ++q) {
+            if (q >= d) break;
+            const double v = warp_sum(yval(q));
             if ((tid & 31) == 0) {
-              if (a) atomicAdd(a + q, v); else atomicAdd(sums + (size_t)l * d + q, v);
+              if (fixed) km_add_fixed(a + q, v * fx_scale);
+              else if (a) atomicAdd(a + q, v); else atomicAdd(sums + (size_t)l * d + q, v);
             }
           }
           if ((tid & 31) == 0) {
-            if (a) atomicAdd(a + d, 32.0); else atomicAdd(counts + l, 32.0);
+            if (fixed) atomicAdd(reinterpret_cast<unsigned int*>(a + d), 32u);
+            else if (a) atomicAdd(a + d, 32.0); else atomicAdd(counts + l, 32.0);
           }
         } else if (live) {
-          if (a) {
+          if (fixed) {
+#pragma unroll
+            for (int q = 0; q < DP; ++q)
+              if (q < d) km_add_fixed(a + q, yval(q) * fx_scale);
+            atomicAdd(reinterpret_cast<unsigned int*>(a + d), 1u);
+          } else if (a) {
             for (int q = 0; q < d; ++q) atomicAdd(a + q, (double)yrow[q]);
             atomicAdd(a + d, 1.0);
           } else {
@@ -229,9 +281,18 @@ kmeans_step_kernel(const T* __restrict__ Y, int64_t n, int d, int64_t ld,
     __syncthreads();
     for (int i = tid; i < k * (d + 1); i += kKmThreads) {
       double v = 0.0;
-      for (int c = 0; c < plan.smem_acc; ++c) v += acc_s[(size_t)c * k * (d + 1) + i];
+      const int j = i / (d + 1), q = i - j * (d + 1);
+      if (fixed) {
+        long long tot = 0;
+        for (int c = 0; c < plan.smem_acc; ++c) {
+          const uint2 w = *reinterpret_cast<const uint2*>(&acc_s[(size_t)c * k * (d + 1) + i]);
+          tot += (long long)(((unsigned long long)w.y << 32) | w.x);
+        }
+        v = q < d ? (double)tot * s_scale[1] : (double)tot;
+      } else {
+        for (int c = 0; c < plan.smem_acc; ++c) v += acc_s[(size_t)c * k * (d + 1) + i];
+      }
       if (v != 0.0) {
-        const int j = i / (d + 1), q = i - j * (d + 1);
         if (q < d) atomicAdd(sums + (size_t)j * d + q, v);
         else atomicAdd(counts + j, v);
       }
@@ -336,7 +397,7 @@ __global__ void nearest_merge_kernel(const double* __restrict__ pdist, const int
 template <typename T, int DP>
 static int launch_kmeans(const T* Y, int64_t n, int d, int64_t ld, const double* centers, int k,
                          int32_t* labels, double* sums, double* counts, double* stats, T* gap,
-                         int update_sums, cudaStream_t st) {
+                         int update_sums, const double* y_absmax, cudaStream_t st) {
   const KmSmemPlan plan = km_plan(d, DP, k);
   if (plan.total > kKmSmemBudget) return DCG_E_SHAPE;
   auto kern = kmeans_step_kernel<T, DP>;
@@ -347,7 +408,7 @@ static int launch_kmeans(const T* Y, int64_t n, int d, int64_t ld, const double*
   const int64_t ntiles = ceil_div(n, kKmThreads * km_frames_per_thread(DP));
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, (int64_t)kNumSMs * per_sm));
   kern<<<grid, kKmThreads, plan.total, st>>>(Y, n, d, ld, centers, k, labels, sums, counts, stats,
-                                             gap, update_sums, plan);
+                                             gap, update_sums, y_absmax, plan);
   DCG_LAUNCH_CHECK();
   return 0;
 }
@@ -355,8 +416,8 @@ static int launch_kmeans(const T* Y, int64_t n, int d, int64_t ld, const double*
 template <typename T>
 static int dispatch_kmeans(const T* Y, int64_t n, int d, int64_t ld, const double* centers, int k,
                            int32_t* labels, double* sums, double* counts, double* stats, T* gap,
-                           int update_sums, cudaStream_t st) {
-#define DCG_KM(DPV) return launch_kmeans<T, DPV>(Y, n, d, ld, centers, k, labels, sums, counts, stats, gap, update_sums, st)
+                           int update_sums, const double* y_absmax, cudaStream_t st) {
+#define DCG_KM(DPV) return launch_kmeans<T, DPV>(Y, n, d, ld, centers, k, labels, sums, counts, stats, gap, update_sums, y_absmax, st)
   if (d <= 4) DCG_KM(4);
   if (d <= 8) DCG_KM(8);
   if (d <= 12) DCG_KM(12);
@@ -375,7 +436,7 @@ extern "C" size_t dcg_kmeans_workspace_bytes(int64_t, int, int, int) { return 25
 extern "C" int dcg_kmeans_step(const void* Y, int64_t n, int d, int64_t ld, int dtype_bytes,
                                const double* centers, int k, int32_t* labels,
                                double* sums, double* counts, double* stats, void* gap,
-                               int update_sums, void* ws, size_t ws_bytes, void* stream) {
+                               int update_sums, const double* y_absmax, void* ws, size_t ws_bytes, void* stream) {
   (void)ws; (void)ws_bytes;
   if (!Y || !centers || !labels || !stats) return DCG_E_NULL;
   if (update_sums && (!sums || !counts)) return DCG_E_NULL;
@@ -394,9 +455,9 @@ extern "C" int dcg_kmeans_step(const void* Y, int64_t n, int d, int64_t ld, int 
   }
   if (dtype_bytes == 4)
     return dispatch_kmeans<float>((const float*)Y, n, d, ld, centers, k, labels, sums, counts, stats,
-                                  (float*)gap, update_sums, st);
+                                  (float*)gap, update_sums, y_absmax, st);
   return dispatch_kmeans<double>((const double*)Y, n, d, ld, centers, k, labels, sums, counts, stats,
-                                 (double*)gap, update_sums, st);
+                                 (double*)gap, update_sums, y_absmax, st);
 }
 
 extern "C" int dcg_kmeans_update(const double* sums, const double* counts, int k, int d,
@@ -410,14 +471,14 @@ extern "C" int dcg_kmeans_update(const double* sums, const double* counts, int k
 
 extern "C" int dcg_kmeans_iterate(const void* Y, int64_t n, int d, int64_t ld, int dtype_bytes,
                                   double* centers, int k, int32_t* labels, double* work,
-                                  void* ws, size_t ws_bytes, void* stream) {
+                                  const double* y_absmax, void* ws, size_t ws_bytes, void* stream) {
   if (!work) return DCG_E_NULL;
   double* sums = work;
   double* counts = work + (size_t)k * d;
   double* stats = counts + k;
   double* info = stats + 3;
   const int rc = dcg_kmeans_step(Y, n, d, ld, dtype_bytes, centers, k, labels, sums, counts, stats, nullptr,
-                                 1, ws, ws_bytes, stream);
+                                 1, y_absmax, ws, ws_bytes, stream);
   if (rc) return rc;
   return dcg_kmeans_update(sums, counts, k, d, centers, info, stream);
 }

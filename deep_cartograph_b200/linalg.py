@@ -146,14 +146,17 @@ def _cholesky_eigh(C0: torch.Tensor, Ct: torch.Tensor, reg: float, out: int):
     Ct v = lambda B v); the dense route is the fallback and the small-F path."""
     F = C0.shape[-1]
     B = C0 + reg * torch.eye(F, dtype=C0.dtype, device=C0.device)
-    L, info = torch.linalg.cholesky_ex(B)
-    if int(info.abs().max().item()) != 0:
-        raise RuntimeError("TICA: C0 + reg*I is not positive definite")
     out = min(out, F)
     got = None
     if F >= _PARTIAL_MIN_F and 2 * (out + 8) < F:
+        # accepted only with residual-checked Ritz pairs of (Ct, B), from Cholesky factorisations
+        # of sigma B - Ct and X^T B X; a B that is not positive definite (or not finite) ends up
+        # on the dense route below, whose Cholesky of B raises as the reference's does
         got = _shift_invert_topk(B, Ct, out)
     if got is None:
+        L, info = torch.linalg.cholesky_ex(B)
+        if int(info.abs().max().item()) != 0:
+            raise RuntimeError("TICA: C0 + reg*I is not positive definite")
         EIG_STATS["dense"] += 1 if C0.dim() == 2 else C0.shape[0]
         Y = torch.linalg.solve_triangular(L, Ct, upper=False)             # L^-1 Ct
         A = torch.linalg.solve_triangular(L, Y.mT, upper=False).mT        # (L^-1 (L^-1 Ct)^T)^T

@@ -101,6 +101,9 @@ def kmeans_lloyd(Y: torch.Tensor, init_centers: torch.Tensor, max_iter: int = 30
     var = s2 / n_tot - (sc / n_tot) ** 2
     tol_eff = float(var.mean().item()) * tol
     C = C - x_mean
+    # bound on |Yc| of this shard: lets the E-step accumulate its partial sums in exact 64-bit
+    # fixed point (native shared-memory integer adds) instead of FP64 compare-and-swap loops
+    absmax = Yc.abs().amax().to(torch.float64).reshape(1) if n > 0 else None
 
     labels = torch.full((n,), -1, dtype=torch.int32, device=dev)
     strict = False
@@ -111,11 +114,11 @@ def kmeans_lloyd(Y: torch.Tensor, init_centers: torch.Tensor, max_iter: int = 30
     for it in range(max_iter):
         if shards is None:
             # single device: memset + E-step + FP64 sums + M-step finish in one library call
-            res = ops.kmeans_iterate_(Yc, C, labels, work)
+            res = ops.kmeans_iterate_(Yc, C, labels, work, absmax=absmax)
             sums, counts = res["sums"], res["counts"]
             changed, _, _, n_empty, shift_tot = work[k * d + k:k * d + k + 5].tolist()   # ONE host read
         else:
-            res = ops.kmeans_step(Yc, C, labels, update_sums=True, want_gap=False)
+            res = ops.kmeans_step(Yc, C, labels, update_sums=True, want_gap=False, absmax=absmax)
             packed = shards.allreduce_sum_(torch.cat([res["sums"].reshape(-1), res["counts"], res["stats"]]))
             sums = packed[:k * d].view(k, d)
             counts = packed[k * d:k * d + k]

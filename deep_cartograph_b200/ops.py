@@ -260,10 +260,22 @@ def _dtype_bytes(t: torch.Tensor) -> int:
     raise TypeError(f"expected float32 or float64, got {t.dtype}")
 
 
+def _absmax_ptr(absmax: Optional[torch.Tensor], device) -> Optional[int]:
+    if absmax is None:
+        return None
+    if not (isinstance(absmax, torch.Tensor) and absmax.is_cuda and absmax.dtype == torch.float64
+            and absmax.numel() == 1 and absmax.device == device):
+        raise TypeError("absmax must be a one-element float64 CUDA tensor on the device of Y")
+    return absmax.data_ptr()
+
+
 def kmeans_step(Y: torch.Tensor, centers: torch.Tensor, labels: torch.Tensor,
-                update_sums: bool = True, want_gap: bool = False) -> dict:
+                update_sums: bool = True, want_gap: bool = False,
+                absmax: Optional[torch.Tensor] = None) -> dict:
     """One Lloyd E-step (+ M-step sums).  ``labels`` (int32) holds the previous labels and is
-    overwritten.  Returns dict(sums, counts, changed, inertia, ties, gap)."""
+    overwritten.  ``absmax`` (one float64 on the device, optional): a bound on ``|Y|`` that switches
+    the partial sums to exact 64-bit fixed point (see dcg.h).
+    Returns dict(sums, counts, changed, inertia, ties, gap)."""
     _need_cuda("Y", Y)
     _need_cuda("centers", centers, torch.float64)
     _need_cuda("labels", labels, torch.int32)
@@ -282,7 +294,7 @@ def kmeans_step(Y: torch.Tensor, centers: torch.Tensor, labels: torch.Tensor,
     ws = _ws(256, dev)
     _lib.call("dcg_kmeans_step", Y.data_ptr(), n, d, ld, _dtype_bytes(Y), centers.data_ptr(), k,
               labels.data_ptr(), _ptr(sums), _ptr(counts), stats.data_ptr(), _ptr(gap),
-              1 if update_sums else 0, ws.data_ptr(), ws.numel(), _stream())
+              1 if update_sums else 0, _absmax_ptr(absmax, dev), ws.data_ptr(), ws.numel(), _stream())
     _count(1)
     return {"sums": sums, "counts": counts, "stats": stats, "gap": gap}
 
@@ -312,7 +324,7 @@ def kmeans_work(k: int, d: int, device) -> torch.Tensor:
 
 
 def kmeans_iterate_(Y: torch.Tensor, centers: torch.Tensor, labels: torch.Tensor,
-                    work: torch.Tensor) -> dict:
+                    work: torch.Tensor, absmax: Optional[torch.Tensor] = None) -> dict:
     """One whole Lloyd iteration on one device in ONE library call (memset, E-step + FP64 sums,
     M-step finish): ``centers`` (k x d FP64) and ``labels`` are updated in place.  Returns views
     into ``work``: sums, counts, stats [changed, inertia, ties], info [n_empty, shift]."""
@@ -328,7 +340,8 @@ def kmeans_iterate_(Y: torch.Tensor, centers: torch.Tensor, labels: torch.Tensor
     if ws is None:
         ws = _KM_WS[Y.device] = _ws(256, Y.device)
     _lib.call("dcg_kmeans_iterate", Y.data_ptr(), n, d, ld, _dtype_bytes(Y), centers.data_ptr(), k,
-              labels.data_ptr(), work.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+              labels.data_ptr(), work.data_ptr(), _absmax_ptr(absmax, Y.device), ws.data_ptr(), ws.numel(),
+              _stream())
     _count(2)
     o = k * d
     return {"sums": work[:o].view(k, d), "counts": work[o:o + k], "stats": work[o + k:o + k + 3],

@@ -120,12 +120,17 @@ int dcg_project_blocks_f32(const float* X, int64_t n, int f, int64_t ld,
  * stats[2] = number of exact ties (FP64 second-best == best).  gap (n, may be NULL) receives
  * second-best minus best score per frame in `dtype_bytes` precision.  Limits: 1 <= d <= 32,
  * k*(pad4(d)+1)*4 bytes <= 200 KB (centres live in shared memory).
- * update_sums = 0 skips sums/counts (final E-step, _kmeans.py:742-754).                         */
+ * update_sums = 0 skips sums/counts (final E-step, _kmeans.py:742-754).
+ * y_absmax (device pointer to one double, may be NULL): a bound |Y[t,q]| <= *y_absmax over the
+ * frames of this call.  With it the per-CTA partial sums are accumulated in 64-bit fixed point
+ * (native 32-bit shared-memory integer adds instead of FP64 compare-and-swap loops): exact integer
+ * sums, order-independent, each value rounded at <= 2^-45 * y_absmax (for <= 128 k frames per CTA),
+ * i.e. below the run-to-run noise of FP64 summation order.  NULL keeps FP64 atomics.            */
 size_t dcg_kmeans_workspace_bytes(int64_t n, int d, int k, int dtype_bytes);
 int dcg_kmeans_step(const void* Y, int64_t n, int d, int64_t ld, int dtype_bytes,
                     const double* centers, int k, int32_t* labels,
                     double* sums, double* counts, double* stats, void* gap,
-                    int update_sums, void* ws, size_t ws_bytes, void* stream);
+                    int update_sums, const double* y_absmax, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- K1: M-step finish ------------------------------------------------------------------------
  * Replaces sklearn `_average_centers` + the centre-shift test of `_kmeans_single_lloyd`
@@ -144,7 +149,7 @@ int dcg_kmeans_update(const double* sums, const double* counts, int k, int d,
  * out empty (info[0] > 0).  Sharded runs call the two halves around their all-reduce instead.   */
 int dcg_kmeans_iterate(const void* Y, int64_t n, int d, int64_t ld, int dtype_bytes,
                        double* centers, int k, int32_t* labels, double* work,
-                       void* ws, size_t ws_bytes, void* stream);
+                       const double* y_absmax, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- K3: nearest sample to each centre -------------------------------------------------------
  * Replaces `statistics.find_centroids` (statistics.py:370-377): argmin_t ||y_t - c_j||_2 per

@@ -112,7 +112,7 @@ def _kmeans_worker(rank, world, port, out):
         from deep_cartograph_b200.modules.statistics import statistics
         from deep_cartograph_b200.parallel import FrameShards, shard_range
 
-        def fake_step(Y, C, labels, update_sums=True, want_gap=False):
+        def fake_step(Y, C, labels, update_sums=True, want_gap=False, absmax=None):
             lab, best, second = oracle.kmeans_assign(Y.numpy(), C.numpy())
             old = labels.numpy().copy()
             labels.copy_(torch.from_numpy(lab))

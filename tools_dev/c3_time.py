@@ -63,12 +63,11 @@ for rep in range(2):
     t.append(ev())
     mean, rng = calc._norm_on_device()
     T1f = T1.to(torch.float32)
-    parts = []
+    Wc = torch.zeros((f, 5), dtype=torch.float32, device=dev)
     c = 0
     for (s0, e0) in chunks:
-        Pc, _, _ = ops.project(calc.training_data[:, s0:e0], T1f[s0:e0, c:c + 5].contiguous(), mean[s0:e0], rng[s0:e0], minmax=False)
-        parts.append(Pc); c += 5
-    P = torch.cat(parts, dim=1)
+        Wc[s0:e0] = T1f[s0:e0, c:c + 5]; c += 5
+    P = ops.project_blocks(calc.training_data, Wc, f // 10, mean, rng)      # all blocks, one pass over X
     t.append(ev())
     s2 = ops.lagged_covariance(P, lag)
     t.append(ev())

@@ -44,7 +44,8 @@ else:
     Y = (cen[idx] + 0.03 * torch.randn((n, d), generator=g, device=dev)).contiguous()
     C = Y[:k].to(torch.float64).clone()
     labels = torch.full((n,), -1, dtype=torch.int32, device=dev)
-    ms = timeit(lambda: ops.kmeans_step(Y, C, labels), reps)
+    bound = Y.abs().amax().to(torch.float64).reshape(1) if os.environ.get("KM_FIXED", "1") == "1" else None
+    ms = timeit(lambda: ops.kmeans_step(Y, C, labels, absmax=bound), reps)
     by = (4.0 * d + 4.0) * n
     fl = 2.0 * k * d * n
     print(f"kmeans n={n} d={d} k={k}: {ms:.3f} ms  {n / ms / 1e3:.1f} Mframes/s  {by / ms / 1e6:.0f} GB/s ({by / ms / 1e6 / HBM * 100:.1f}% HBM)  {fl / ms / 1e9:.1f} TFLOP/s fp32-equivalent")
