@@ -84,7 +84,10 @@ __device__ __forceinline__ void km_add_fixed(double* slot, double v) {
   if (hi != 0) atomicAdd(reinterpret_cast<int*>(w + 1), hi);
 }
 
-template <typename T, int DP>
+// DP = padded centre row in shared memory (multiple of 4 floats); DU <= DP = dimensions that enter
+// the FMA chain (DU == d when d has its own instantiation, e.g. C5's d = 10 with DP = 12: 10 FMAs
+// per score instead of 12; otherwise DU == DP and the padding multiplies zeros).
+template <typename T, int DP, int DU>
 __global__ void __launch_bounds__(kKmThreads, 1)
 kmeans_step_kernel(const T* __restrict__ Y, int64_t n, int d, int64_t ld,
                    const double* __restrict__ centers, int k, int32_t* __restrict__ labels,
@@ -187,7 +190,7 @@ kmeans_step_kernel(const T* __restrict__ Y, int64_t n, int d, int64_t ld,
       for (int r = 0; r < kKmR; ++r) {
         float dot = 0.f;
 #pragma unroll
-        for (int q = 0; q < DP; ++q) dot = fmaf(x[r][q], c[q], dot);
+        for (int q = 0; q < DU; ++q) dot = fmaf(x[r][q], c[q], dot);
         const float s = fmaf(-2.f, dot, csq);
         second[r] = fminf(second[r], fmaxf(s, best[r]));
         lab[r] = (s < best[r]) ? j : lab[r];
@@ -394,13 +397,13 @@ __global__ void nearest_merge_kernel(const double* __restrict__ pdist, const int
   argmin[j] = bi;
 }
 
-template <typename T, int DP>
+template <typename T, int DP, int DU = DP>
 static int launch_kmeans(const T* Y, int64_t n, int d, int64_t ld, const double* centers, int k,
                          int32_t* labels, double* sums, double* counts, double* stats, T* gap,
                          int update_sums, const double* y_absmax, cudaStream_t st) {
   const KmSmemPlan plan = km_plan(d, DP, k);
   if (plan.total > kKmSmemBudget) return DCG_E_SHAPE;
-  auto kern = kmeans_step_kernel<T, DP>;
+  auto kern = kmeans_step_kernel<T, DP, DU>;
   DCG_CUDA_TRY(ensure_dynamic_smem((const void*)kern, (size_t)(plan.total)));
   int per_sm = 1;
   DCG_CUDA_TRY(cached_occupancy(&per_sm, (const void*)kern, kKmThreads, plan.total));
@@ -420,6 +423,7 @@ static int dispatch_kmeans(const T* Y, int64_t n, int d, int64_t ld, const doubl
 #define DCG_KM(DPV) return launch_kmeans<T, DPV>(Y, n, d, ld, centers, k, labels, sums, counts, stats, gap, update_sums, y_absmax, st)
   if (d <= 4) DCG_KM(4);
   if (d <= 8) DCG_KM(8);
+  if (d == 10) return launch_kmeans<T, 12, 10>(Y, n, d, ld, centers, k, labels, sums, counts, stats, gap, update_sums, y_absmax, st);
   if (d <= 12) DCG_KM(12);
   if (d <= 16) DCG_KM(16);
   if (d <= 24) DCG_KM(24);
