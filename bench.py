@@ -163,7 +163,7 @@ def run_reference_arm(args):
             "config": workload_config(args, args.gpus, "cpu"),
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit_json(line)
 
 
 def workload_config(args, world, engine):
@@ -177,8 +177,32 @@ def workload_config(args, world, engine):
 # ----------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------
+_JSON_FD = None
+
+
+def _quiet_stdout():
+    """stdout carries exactly ONE JSON line: libraries that write to file descriptor 1 from native
+    code (NCCL prints its version banner there) are sent to stderr; the JSON line goes to the
+    original descriptor."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json(line) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, data)
+
+
 def main():
     args = parse_args()
+    _quiet_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
         return
@@ -418,7 +442,7 @@ def main():
                 "data": "synthetic", "config": workload_config(args, world, engine),
                 "roofline": roofline, "passes": passes, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
                 "clocks": clocks, "eigenvalues": [float(v) for v in evals.cpu().tolist()]}
-        print(json.dumps(line), flush=True)
+        emit_json(line)
     if shards is not None:
         dist.destroy_process_group()
 
