@@ -743,10 +743,22 @@ class DeepTICACalculator(CVCalculator):
 
     def train(self) -> bool:
         from .deep_tica import DeepTICA
+        from .deep_tica import allreduce_gradients_
         X = self.training_data
         dev = X.device
         lag = int(self.configuration.get("lag_time") or 1)
-        M = X.shape[0] - lag
+        sh = self.shards
+        if sh is not None:
+            # frame-sharded training (exact all-reduce): own rows + lag halo; every rank
+            # runs the same number of equally sized local minibatches (the loss has collectives),
+            # so all ranks use the smallest local pair count
+            X = sh.with_halo(X, lag)
+            M_loc = X.shape[0] - lag
+            mt = torch.tensor([float(M_loc)], dtype=torch.float64, device=dev)
+            torch.distributed.all_reduce(mt, op=torch.distributed.ReduceOp.MIN, group=sh.group)
+            M = int(mt.item())
+        else:
+            M = X.shape[0] - lag
         if M < 4:
             logger.error("Not enough frames to build time-lagged pairs.")
             return False
@@ -774,9 +786,10 @@ class DeepTICACalculator(CVCalculator):
                 for b in self._epoch_batches(tr_idx, gen, self.shuffle):
                     if b.numel() <= d + 1:
                         continue
-                    loss, _ = model.loss(X[b], X[b + lag])
+                    loss, _ = model.loss(X[b], X[b + lag], shards=sh)
                     opt.zero_grad(set_to_none=True)
                     loss.backward()
+                    allreduce_gradients_(model.nn, sh)
                     opt.step()
                     tot += float(loss.detach()); nb += 1
                 if (epoch + 1) % self.check_val_every:
@@ -787,7 +800,7 @@ class DeepTICACalculator(CVCalculator):
                     for b in self._epoch_batches(va_idx, gen, False):
                         if b.numel() <= d + 1:
                             continue
-                        vl, _ = model.loss(X[b], X[b + lag])
+                        vl, _ = model.loss(X[b], X[b + lag], shards=sh)
                         vt += float(vl); vn += 1
                 last_val = vt / max(vn, 1)
                 history.append({"epoch": epoch + 1, "train_loss": tot / max(nb, 1), "valid_loss": last_val})
@@ -801,7 +814,7 @@ class DeepTICACalculator(CVCalculator):
             if last_val is None:                             # never validated: validate once
                 model.eval()
                 with torch.no_grad():
-                    last_val = float(model.loss(X[va_idx], X[va_idx + lag])[0]) if va_idx.numel() > d + 1 else float("nan")
+                    last_val = float(model.loss(X[va_idx], X[va_idx + lag], shards=sh)[0]) if va_idx.numel() > d + 1 else float("nan")
                 best_val = last_val
             score = best_val if self.model_to_save == "best" else last_val
             ok = bool(np.isfinite(score)) and score >= -float(d) - 1e-6      # reference :1624-1626
@@ -830,13 +843,23 @@ class DeepTICACalculator(CVCalculator):
             return
         # linear TICA read-out from the whole training set, streamed in batches (FP64 raw sums)
         X, lag = self.training_data, int(self.configuration.get("lag_time") or 1)
+        if self.shards is not None:
+            X = self.shards.with_halo(X, lag)
         M = X.shape[0] - lag
         acc = None
         with torch.no_grad():
             for s0 in range(0, M, 1 << 16):
                 e0 = min(M, s0 + (1 << 16))
-                s = ops.ticacov_sums(self.cv.features(X[s0:e0]), self.cv.features(X[s0 + lag:e0 + lag]))
-                acc = s if acc is None else {k: acc[k] + s[k] for k in s}
+                s = ops.ticacov_sums(self.cv.features(X[s0:e0]), self.cv.features(X[s0 + lag:e0 + lag]))["flat"]
+                acc = s if acc is None else acc + s
+            if self.shards is not None:                          # global sums and pair count
+                acc = self.shards.allreduce_sum_(torch.cat([acc, torch.tensor([float(M)], dtype=torch.float64,
+                                                                                device=acc.device)]))
+                M = int(round(float(acc[-1].item())))
+                acc = acc[:-1]
+            d_, o_ = self.cv_dimension, 2 + self.cv_dimension
+            acc = {"swf": acc[2:o_], "sff": acc[o_:o_ + d_ * d_].view(d_, d_),
+                   "sfg": acc[o_ + d_ * d_:o_ + 2 * d_ * d_].view(d_, d_), "slg": acc[o_ + 2 * d_ * d_ + d_:]}
             evals, V = linalg.tica_from_sums(acc["sff"], acc["sfg"], acc["swf"], acc["slg"], M,
                                              self.cv_dimension, self.reg)
             self.cv.tica_mean.copy_((acc["swf"] / M).to(torch.float32))

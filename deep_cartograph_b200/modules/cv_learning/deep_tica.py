@@ -7,6 +7,13 @@ weighted mean, mean-free C0 / C_tau of the network outputs, Cholesky-reduced eig
 
 The B x d reduction runs in one CUDA kernel (``dcg_ticacov_f32``, FP64 sums); its backward is
 analytic; the d x d Cholesky / eigh stay in ``torch.linalg`` (autograd supplies dL/dC0, dL/dCt).
+
+Frame-sharded training ("exact all-reduce"): C0 / C_tau are statistics of
+the WHOLE minibatch, so with the minibatch split over ranks the raw sums are all-reduced before
+the eigen step (``shards``: 2 + 3d + 2d^2 doubles) and every rank evaluates the same loss; the
+backward needs one more all-reduce of d doubles (the gradient through the batch mean), and the
+parameter gradients are SUMMED over ranks (``allreduce_gradients_``) -- the result equals the
+single-process gradient of the loss on the concatenated minibatch.
 """
 from __future__ import annotations
 
@@ -22,8 +29,11 @@ class _TicaCov(torch.autograd.Function):
     """(f, g, w, wl) -> (C0, Ct) in float64, mean-free with mu = sum_n w_n f_n / sum w."""
 
     @staticmethod
-    def forward(ctx, f, g, w, wl):
+    def forward(ctx, f, g, w, wl, shards=None):
         s = ops.ticacov_sums(f.detach(), g.detach(), w, wl)
+        if shards is not None:
+            shards.allreduce_sum_(s["flat"])          # the views below see the global sums
+        ctx.shards = shards
         sw, swl = s["sw"], s["swl"]
         mu = s["swf"] / sw
         C0 = s["sff"] / sw - torch.outer(mu, mu)
@@ -50,15 +60,33 @@ class _TicaCov(torch.autograd.Function):
         d_gt = wln[:, None] * (ft @ Ht)
         # mean subtraction: f~ = f - mu, g~ = g - mu, mu = sum wn f
         tot = d_ft.sum(dim=0) + d_gt.sum(dim=0)
+        if ctx.shards is not None:
+            ctx.shards.allreduce_sum_(tot)            # mu is the mean of the WHOLE minibatch
         d_f = d_ft - wn[:, None] * tot
-        return d_f.to(dt), d_gt.to(dt), None, None
+        return d_f.to(dt), d_gt.to(dt), None, None, None
 
 
 def tica_covariances(f: torch.Tensor, g: torch.Tensor, w: Optional[torch.Tensor] = None,
-                     wl: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+                     wl: Optional[torch.Tensor] = None, shards=None) -> Tuple[torch.Tensor, torch.Tensor]:
     """Mean-free, symmetrised C0 and C_tau (float64, d x d) of the outputs f = nn(x_t),
-    g = nn(x_{t+lag}) (float32, B x d), differentiable w.r.t. f and g."""
-    return _TicaCov.apply(f.contiguous(), g.contiguous(), w, wl)
+    g = nn(x_{t+lag}) (float32, B x d), differentiable w.r.t. f and g.  With ``shards``
+    (parallel.FrameShards) f and g are this rank's part of the minibatch and C0 / C_tau are those
+    of the whole minibatch (identical on every rank)."""
+    return _TicaCov.apply(f.contiguous(), g.contiguous(), w, wl, shards)
+
+
+def allreduce_gradients_(module: nn.Module, shards) -> None:
+    """SUM the parameter gradients over ranks in one fused collective (the loss is a function of
+    the global minibatch: dL/dtheta = sum over ranks of the local chain-rule terms)."""
+    grads = [p.grad for p in module.parameters() if p.grad is not None]
+    if not grads or shards is None:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    shards.allreduce_sum_(flat)
+    o = 0
+    for g in grads:
+        g.copy_(flat[o:o + g.numel()].view_as(g))
+        o += g.numel()
 
 
 def reduced_eigenvalues(C0: torch.Tensor, Ct: torch.Tensor, reg: float) -> torch.Tensor:
@@ -72,9 +100,9 @@ def reduced_eigenvalues(C0: torch.Tensor, Ct: torch.Tensor, reg: float) -> torch
 
 
 def tica_loss(f: torch.Tensor, g: torch.Tensor, w: Optional[torch.Tensor] = None,
-              wl: Optional[torch.Tensor] = None, reg: float = 1e-6, n_eig: int = 0):
+              wl: Optional[torch.Tensor] = None, reg: float = 1e-6, n_eig: int = 0, shards=None):
     """DeepTICA loss ``-sum lambda_i^2`` and the eigenvalues (descending)."""
-    C0, Ct = tica_covariances(f, g, w, wl)
+    C0, Ct = tica_covariances(f, g, w, wl, shards)
     evals = reduced_eigenvalues(C0, Ct, reg)
     used = evals[:n_eig] if n_eig and n_eig > 0 else evals
     return -(used ** 2).sum(), evals
@@ -111,8 +139,8 @@ class DeepTICA(nn.Module):
         z = (self.features(x) - self.tica_mean) @ self.tica_evecs
         return (z - self.out_mean) / self.out_range
 
-    def loss(self, x_t: torch.Tensor, x_lag: torch.Tensor, w=None, wl=None):
-        return tica_loss(self.features(x_t), self.features(x_lag), w, wl, reg=self.reg)
+    def loss(self, x_t: torch.Tensor, x_lag: torch.Tensor, w=None, wl=None, shards=None):
+        return tica_loss(self.features(x_t), self.features(x_lag), w, wl, reg=self.reg, shards=shards)
 
     @torch.no_grad()
     def fit_tica_layer(self, x_t: torch.Tensor, x_lag: torch.Tensor):

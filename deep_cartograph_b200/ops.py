@@ -390,6 +390,6 @@ def ticacov_sums(f: torch.Tensor, g: torch.Tensor, w: Optional[torch.Tensor] = N
               out.data_ptr(), _stream())
     _count(1)
     o = 2 + d
-    return {"sw": out[0], "swl": out[1], "swf": out[2:o],
+    return {"flat": out, "sw": out[0], "swl": out[1], "swf": out[2:o],
             "sff": out[o:o + d * d].view(d, d), "sfg": out[o + d * d:o + 2 * d * d].view(d, d),
             "slf": out[o + 2 * d * d:o + 2 * d * d + d], "slg": out[o + 2 * d * d + d:]}

@@ -179,3 +179,85 @@ def test_shard_range_partitions_all_frames():
         rs = [shard_range(n, r, w) for r in range(w)]
         assert rs[0][0] == 0 and rs[-1][1] == n
         assert all(rs[i][1] == rs[i + 1][0] for i in range(w - 1))
+
+
+def _cpu_ticacov_sums(f, g, w=None, wl=None):
+    """CPU stand-in for ops.ticacov_sums (the kernel's output layout, dcg.h)."""
+    f64, g64 = f.double(), g.double()
+    B, d = f.shape
+    w64 = torch.ones(B, dtype=torch.float64) if w is None else w.double()
+    wl64 = torch.ones(B, dtype=torch.float64) if wl is None else wl.double()
+    out = torch.cat([w64.sum().reshape(1), wl64.sum().reshape(1), (w64[:, None] * f64).sum(0),
+                     ((w64[:, None] * f64).T @ f64).reshape(-1), ((wl64[:, None] * f64).T @ g64).reshape(-1),
+                     (wl64[:, None] * f64).sum(0), (wl64[:, None] * g64).sum(0)])
+    o = 2 + d
+    return {"flat": out, "sw": out[0], "swl": out[1], "swf": out[2:o],
+            "sff": out[o:o + d * d].view(d, d), "sfg": out[o + d * d:o + 2 * d * d].view(d, d),
+            "slf": out[o + 2 * d * d:o + 2 * d * d + d], "slg": out[o + 2 * d * d + d:]}
+
+
+def _deeptica_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from deep_cartograph_b200 import ops
+        from deep_cartograph_b200.modules.cv_learning import deep_tica
+        from deep_cartograph_b200.parallel import FrameShards, shard_range
+        ops.ticacov_sums = _cpu_ticacov_sums
+        deep_tica.ops.ticacov_sums = _cpu_ticacov_sums
+        torch.manual_seed(11)
+        B, F, d = 301, 12, 3
+        # slowly varying inputs so that C_tau is well conditioned
+        base = torch.cumsum(torch.randn(B + 5, F), dim=0) * 0.1
+        x_t, x_lag = base[:B].float(), base[5:B + 5].float()
+        net = torch.nn.Sequential(torch.nn.Linear(F, 8), torch.nn.Tanh(), torch.nn.Linear(8, d))
+        ref = [p.detach().clone() for p in net.parameters()]
+        # single process: the whole minibatch
+        loss_all, ev_all = deep_tica.tica_loss(net(x_t), net(x_lag), reg=1e-6)
+        loss_all.backward()
+        g_all = [p.grad.detach().clone() for p in net.parameters()]
+        for p in net.parameters():
+            p.grad = None
+        # sharded: this rank's part of the minibatch, sums all-reduced
+        s, e = shard_range(B, rank, world)
+        shards = FrameShards()
+        loss_loc, ev_loc = deep_tica.tica_loss(net(x_t[s:e]), net(x_lag[s:e]), reg=1e-6, shards=shards)
+        loss_loc.backward()
+        deep_tica.allreduce_gradients_(net, shards)
+        assert abs(float(loss_loc) - float(loss_all)) <= 1e-10 * abs(float(loss_all)), (float(loss_loc), float(loss_all))
+        np.testing.assert_allclose(ev_loc.detach().numpy(), ev_all.detach().numpy(), rtol=1e-10)
+        # the last bias has an analytically zero gradient (the covariances are mean-free): absolute
+        # tolerance on the scale of the largest gradient
+        gmax = max(float(ga.abs().max()) for ga in g_all)
+        for p, ga, r in zip(net.parameters(), g_all, ref):
+            assert torch.equal(p.detach(), r)
+            np.testing.assert_allclose(p.grad.numpy(), ga.numpy(), rtol=2e-4, atol=2e-6 * gmax)
+        out.put((rank, "ok"))
+    except Exception:  # noqa: BLE001
+        import traceback
+        out.put((rank, "FAIL: " + traceback.format_exc()))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_sharded_deeptica_loss_and_gradients_world2():
+    """SURVEY 8e, DeepTICA "exact all-reduce": with the minibatch split over two ranks the loss,
+    the eigenvalues and the (summed) parameter gradients equal those of the whole minibatch in one
+    process.  The correlation-sum kernel is emulated on the CPU."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 33500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_deeptica_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(240)
+    results = [out.get(timeout=5) for _ in range(world)]
+    for p in procs:
+        assert p.exitcode == 0, results
+    assert sorted(r[1] for r in results) == ["ok"] * world, results
