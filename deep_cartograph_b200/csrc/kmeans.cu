@@ -13,7 +13,9 @@
 //
 // Roofline: 4*d (or 8*d) bytes read + 4 bytes written per frame, 2*k*d FLOPs: HBM-bound for
 // k <~ 24, FP32-FMA-bound beyond (k=1000, d=10 is 500 FLOP/B).
+#include <cstdlib>
 #include "dcg_common.cuh"
+#include "kmeans_common.cuh"
 
 namespace dcg {
 
@@ -41,47 +43,6 @@ static KmSmemPlan km_plan(int d, int dp, int k) {
   p.smem_acc = (int)std::min<size_t>(room / acc_bytes, kKmThreads / 32);
   p.total = o + (size_t)p.smem_acc * acc_bytes;
   return p;
-}
-
-// FP64 re-evaluation of one frame over all centres (rare path), by the whole warp: the frame is
-// broadcast through shared memory, lane l scores centres l, l + 32, ..., and the partial
-// (best, second, label) triples are merged by shuffles with the lowest-index tie-break.  All lanes
-// return the same result.  (A per-thread loop over k centres kept 31 lanes idle for ~25 k
-// instructions per refined frame: 12 % of all stall samples at k = 1000.)
-__device__ __forceinline__ void km_refine_warp(const double* __restrict__ yy_s, int d,
-                                               const double* __restrict__ centers, int k,
-                                               int& lab, double& best, double& second) {
-  const int lane = threadIdx.x & 31;
-  best = INFINITY; second = INFINITY; lab = 0x7fffffff;
-  for (int j = lane; j < k; j += 32) {
-    const double* c = centers + (size_t)j * d;
-    double dot = 0.0, csq = 0.0;
-    for (int q = 0; q < d; ++q) { const double cq = c[q]; dot = fma(yy_s[q], cq, dot); csq = fma(cq, cq, csq); }
-    const double s = csq - 2.0 * dot;
-    if (s < best) { second = best; best = s; lab = j; }      // j ascending per lane: strict < keeps the lowest
-    else if (s < second) second = s;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-    const double os = __shfl_xor_sync(0xffffffffu, second, o);
-    const int ol = __shfl_xor_sync(0xffffffffu, lab, o);
-    const bool take = ob < best || (ob == best && ol < lab);
-    // second best of the union: the larger of the two bests, or either side's second
-    const double hi = take ? best : ob;
-    second = fmin(fmin(second, os), hi);
-    if (take) { best = ob; lab = ol; }
-  }
-}
-
-// slot (8 bytes of shared memory, two's complement in two 32-bit words) += round(v)
-__device__ __forceinline__ void km_add_fixed(double* slot, double v) {
-  const long long iv = __double2ll_rn(v);
-  const unsigned int lo = (unsigned int)iv;
-  unsigned int* w = reinterpret_cast<unsigned int*>(slot);
-  const unsigned int old = atomicAdd(w, lo);
-  const int hi = (int)(iv >> 32) + (((old + lo) < lo) ? 1 : 0);
-  if (hi != 0) atomicAdd(reinterpret_cast<int*>(w + 1), hi);
 }
 
 // DP = padded centre row in shared memory (multiple of 4 floats); DU <= DP = dimensions that enter
@@ -456,6 +417,17 @@ extern "C" int dcg_kmeans_step(const void* Y, int64_t n, int d, int64_t ld, int 
       DCG_CUDA_TRY(cudaMemsetAsync(sums, 0, (size_t)k * d * sizeof(double), st));
       DCG_CUDA_TRY(cudaMemsetAsync(counts, 0, (size_t)k * sizeof(double), st));
     }
+  }
+  // many centres: the scan runs on the tensor cores (kmeans_tc.cu) when the data bound is known
+  // (DCG_KMEANS_TC: 0 = CUDA cores only, 1 = tcgen05 / TMEM variant, otherwise the register-resident scan)
+  {
+    const char* sel = getenv("DCG_KMEANS_TC");
+    int rc = DCG_E_MODE;
+    if (sel && sel[0] == '1')
+      rc = kmeans_tc_launch(Y, dtype_bytes, n, d, ld, centers, k, labels, sums, counts, stats, gap, update_sums, y_absmax, st);
+    else if (!(sel && sel[0] == '0'))
+      rc = kmeans_mma_launch(Y, dtype_bytes, n, d, ld, centers, k, labels, sums, counts, stats, gap, update_sums, y_absmax, st);
+    if (rc != DCG_E_MODE) return rc;
   }
   if (dtype_bytes == 4)
     return dispatch_kmeans<float>((const float*)Y, n, d, ld, centers, k, labels, sums, counts, stats,
