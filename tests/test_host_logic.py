@@ -46,6 +46,13 @@ def test_argument_errors_without_gpu():
     assert lib.dcg_project_f32(p, 10, 4, 4, None, None, p, 65, p, None, None, p, 1 << 20, None) == -1001
     assert lib.dcg_kmeans_step(p, 10, 40, 40, 4, p, 3, p, p, p, p, None, 1, None, p, 64, None) == -1001
     assert lib.dcg_kmeans_step(p, 10, 4, 4, 2, p, 3, p, p, p, p, None, 1, None, p, 64, None) == -1005
+    # hTICA level-1 block projection: s <= 16, block <= 1018, 16-byte aligned rows
+    assert lib.dcg_project_blocks_f32(p, 10, 8, 8, None, None, p, 4, 17, p, 34, p, 1 << 20, None) == -1001
+    assert lib.dcg_project_blocks_f32(p, 10, 2000, 2000, None, None, p, 1019, 4, p, 8, p, 1 << 20, None) == -1001
+    assert lib.dcg_project_blocks_f32(p, 10, 8, 8, None, None, p, 4, 2, p, 3, p, 1 << 20, None) == -1001   # p_ld too small
+    assert lib.dcg_project_blocks_f32(p, 10, 6, 6, None, None, p, 3, 2, p, 4, p, 1 << 20, None) == -1003   # ld % 4 != 0
+    assert lib.dcg_project_blocks_f32(p, 10, 8, 8, None, None, p, 4, 2, p, 4, None, 0, None) == -1002
+    assert lib.dcg_project_blocks_workspace_bytes(1000, 4950, 495) == 10 * 8 * 8 * 32 * (16 + 4) * 4
     assert lib.dcg_colstats_workspace_bytes(1000, 10) > 0
     assert lib.dcg_cov_workspace_bytes(1000, 1000, 10, 0, 1) >= 256 + 26 * 32     # 16 S_tau + 10 S0 super-tile descriptors
     assert lib.dcg_ticacov_out_doubles(3) == 2 + 3 + 18 + 6
@@ -58,6 +65,7 @@ def test_ops_have_no_cpu_fallback():
                  lambda: ops.standardize_(X, torch.zeros(4), torch.ones(4)),
                  lambda: ops.lagged_covariance(X, 1),
                  lambda: ops.project(X, torch.zeros(4, 2)),
+                 lambda: ops.project_blocks(X, torch.zeros(4, 1), 2),
                  lambda: ops.kmeans_step(X, torch.zeros(2, 4, dtype=torch.float64), torch.zeros(8, dtype=torch.int32)),
                  lambda: ops.nearest_to_centers(X, torch.zeros(2, 4, dtype=torch.float64))):
         with pytest.raises(RuntimeError, match="no CPU fallback"):
