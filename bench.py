@@ -258,7 +258,7 @@ def main():
       with _Timed("stats", record):
         st = ops.column_stats(X)
         if shards is not None:
-            st = shards.merge_stats(st)
+            st = shards.merge_stats(st, n_total=n * world)          # equal shards: no host read
         ntot = st["n"]
         mean = st["mean"].to(torch.float32)
         rng = torch.sqrt(st["m2"] / (ntot - 1)).to(torch.float32)
@@ -273,7 +273,7 @@ def main():
             e1.record()
             cov_ev.append((e0, e1))
         if shards is not None:
-            s = shards.allreduce_sums(s)
+            s = shards.allreduce_sums(s, m_total=n * world - LAG)
       with _Timed("eigen", record):
         evals, V = linalg.tica_from_sums(ops.symmetrize_upper(s["S0"]), s["St"], s["a"], s["b"], s["M"], DIM)
         W = V.to(torch.float32)

@@ -508,7 +508,7 @@ class LinearCalculator(CVCalculator):
         if s is None:
             s = ops.lagged_covariance(X, lag, mean, rng, block=block, engine=engine, want_st=want_st)
         if self.shards is not None:
-            s = self.shards.allreduce_sums(s)
+            s = self.shards.allreduce_sums(s, m_total=(self.num_frames - lag) if self.num_frames else None)
         if not s.get("_S0_full"):
             s["S0"] = ops.symmetrize_upper(s["S0"])
         s.pop("_S0_full", None)

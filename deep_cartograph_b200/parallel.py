@@ -35,10 +35,11 @@ class FrameShards:
         self.world = dist.get_world_size(group)
 
     # ---- statistics ---------------------------------------------------------------------------
-    def merge_stats(self, st: dict) -> dict:
+    def merge_stats(self, st: dict, n_total: Optional[int] = None) -> dict:
         """All-gather the per-rank column statistics and merge them on the device in one shot
         (FP64): N = sum n_r, mean = sum n_r mean_r / N, M2 = sum M2_r + sum n_r (mean_r - mean)^2,
-        min / max over ranks.  One collective, one host read (the global frame count)."""
+        min / max over ranks.  One collective, one host read (the global frame count) -- none when
+        the caller already knows ``n_total`` (repeated passes over the same shards)."""
         f = st["mean"].numel()
         dev = st["mean"].device
         packed = torch.empty(1 + 4 * f, dtype=torch.float64, device=dev)
@@ -60,7 +61,8 @@ class FrameShards:
         inf = torch.full((), float("inf"), dtype=torch.float64, device=dev)
         mn = torch.where(live, allp[:, 1 + 2 * f:1 + 3 * f], inf).min(dim=0).values.to(torch.float32)
         mx = torch.where(live, allp[:, 1 + 3 * f:], -inf).max(dim=0).values.to(torch.float32)
-        return {"n": int(round(float(N.item()))), "mean": mean, "m2": m2, "min": mn, "max": mx}
+        n_all = int(n_total) if n_total is not None else int(round(float(N.item())))
+        return {"n": n_all, "mean": mean, "m2": m2, "min": mn, "max": mx}
 
     # ---- halo ---------------------------------------------------------------------------------
     def with_halo(self, X: torch.Tensor, lag: int) -> torch.Tensor:
@@ -104,8 +106,9 @@ class FrameShards:
         return dist.get_global_rank(self.group, group_rank) if self.group is not None else group_rank
 
     # ---- reductions ---------------------------------------------------------------------------
-    def allreduce_sums(self, s: dict) -> dict:
-        """FP64 SUM all-reduce of one fused buffer [S0 | St | a | b | M]."""
+    def allreduce_sums(self, s: dict, m_total: Optional[int] = None) -> dict:
+        """FP64 SUM all-reduce of one fused buffer [S0 | St | a | b | M].  ``m_total`` (the global
+        number of lagged pairs, n_total - lag) saves the host read of the reduced M."""
         keys = [k for k in ("S0", "St", "a", "b") if s.get(k) is not None]
         dev = s["a"].device
         flat = torch.cat([s[k].reshape(-1) for k in keys] +
@@ -117,7 +120,7 @@ class FrameShards:
             nel = s[k].numel()
             out[k] = flat[o:o + nel].view(s[k].shape)
             o += nel
-        out["M"] = int(round(float(flat[o].item())))
+        out["M"] = int(m_total) if m_total is not None else int(round(float(flat[o].item())))
         return out
 
     def allreduce_minmax(self, mn: torch.Tensor, mx: torch.Tensor):
