@@ -30,6 +30,7 @@ import torch
 from ... import linalg, ops
 from ...parallel import FrameShards
 from ..common import unzip_files, zip_files
+from ..plumed import colvars as colvars_io
 from ..plumed.colvars import create_dataframe_from_files
 
 logger = logging.getLogger(__name__)
@@ -150,6 +151,21 @@ class CVCalculator:
         self.ref_topology_path = ref_topology_path
         if train_topology_paths is not None and self.ref_topology_path is None:
             self.ref_topology_path = train_topology_paths[0]
+        paths = [train_colvars_paths] if isinstance(train_colvars_paths, str) else list(train_colvars_paths)
+        if paths and all(colvars_io.has_fresh_sidecar(p) for p in paths):
+            # binary sidecars: memory-mapped float32 tables, no text parsing, gathered
+            # straight into a pinned buffer that load_training_tensor streams to the device
+            logger.info("Reading training data from binary colvars sidecars...")
+            Xh, names, labels = colvars_io.create_matrix_from_sidecars(paths, features_list=features_list,
+                                                                       **self.training_reading_settings)
+            X = torch.from_numpy(Xh)
+            if torch.cuda.is_available():
+                try:
+                    X = X.pin_memory()
+                except RuntimeError:
+                    pass
+            self.load_training_tensor(X, names, labels)
+            return
         logger.info("Reading training data from colvars files...")
         df = create_dataframe_from_files(colvars_paths=train_colvars_paths,
                                          topology_paths=train_topology_paths,

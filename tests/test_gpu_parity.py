@@ -6,6 +6,7 @@ Tolerances (BASELINE.json north_star): covariances / eigenvalues 1e-5 relative t
 (normwise), eigenvectors 1e-5 up to sign, projections 1e-4, KMeans labels identical from fixed
 initial centroids with exact-tie frames counted and reported.
 """
+import copy
 import os
 
 import numpy as np
@@ -701,6 +702,38 @@ def test_train_colvars_step_api_reproduces_golden(dev, c1, tmp_path, engine):
         np.testing.assert_allclose(calc.cv, c1[f"{cv}_cv_weights"], atol=tol_w[cv])
         np.testing.assert_allclose(calc.features_norm_mean, c1[f"{cv}_features_norm_mean"], atol=2e-7)
         np.testing.assert_allclose(calc.features_norm_range, c1[f"{cv}_features_norm_range"], rtol=1e-6)
+
+
+def test_train_colvars_from_binary_sidecar_equals_text_path(dev, tmp_path):
+    """with a fresh float32 sidecar next to the colvars file the step reads the
+    memory-mapped table (no text parsing) and produces the same models and projections, including
+    the `input_colvars` start / stop / stride slice."""
+    import shutil
+    from deep_cartograph_b200.modules.plumed import colvars as cio
+    from deep_cartograph_b200.modules.cv_learning import CVCalculator
+    from deep_cartograph_b200.tools import train_colvars
+    feats = [l.strip() for l in open(os.path.join(GOLDEN, "peptide_c1_features.txt")) if l.strip()]
+    src = str(tmp_path / "peptide.dat")
+    shutil.copy(os.path.join(GOLDEN, "peptide_c1.dat"), src)
+    cfg = _config("tc_3xtf32")
+    cfg["cvs"] = ["pca", "tica"]
+    cfg["common"]["input_colvars"] = {"start": 2, "stop": 160, "stride": 1}
+    outs = {}
+    for tag in ("text", "sidecar"):
+        if tag == "sidecar":
+            cio.write_sidecar(src)
+            assert cio.has_fresh_sidecar(src)
+        outs[tag] = train_colvars(configuration=copy.deepcopy(cfg), train_colvars_paths=[src],
+                                  trajectory_names=["CA_example"], features_list=feats,
+                                  output_folder=str(tmp_path / f"train_{tag}"))
+    for cv in ("pca", "tica"):
+        a = CVCalculator.load(outs["text"][cv]["model_path"], str(tmp_path / f"la_{cv}"))
+        b = CVCalculator.load(outs["sidecar"][cv]["model_path"], str(tmp_path / f"lb_{cv}"))
+        assert np.array_equal(a.cv, b.cv)
+        assert np.array_equal(a.features_norm_mean, b.features_norm_mean)
+        pa = pd.read_csv(outs["text"][cv]["traj_paths"][0]).to_numpy()
+        pb = pd.read_csv(outs["sidecar"][cv]["traj_paths"][0]).to_numpy()
+        assert np.array_equal(pa, pb)
 
 
 @pytest.mark.parametrize("cv", ["pca", "tica", "htica"])

@@ -256,6 +256,41 @@ def test_colvars_reader_semantics(tmp_path):
     assert "time" not in df3.columns and df3.shape == (164, 54)
 
 
+def test_binary_sidecar_matches_text_reader(tmp_path):
+    """the memory-mapped float32 sidecar gives exactly the matrix, column order and
+    file labels of the text reader for every slice / selection, and goes stale with its source."""
+    import shutil
+    from deep_cartograph_b200.modules.plumed import colvars as cio
+    feats = [l.strip() for l in open(os.path.join(GOLDEN, "peptide_c1_features.txt")) if l.strip()]
+    a = str(tmp_path / "a.dat"); b = str(tmp_path / "b.dat")
+    shutil.copy(os.path.join(GOLDEN, "peptide_c1.dat"), a)
+    shutil.copy(os.path.join(GOLDEN, "peptide_c1.dat"), b)
+    assert not cio.has_fresh_sidecar(a)
+    for p in (a, b):
+        cio.write_sidecar(p, chunk_rows=50)            # several chunks
+        assert cio.has_fresh_sidecar(p)
+    for kw in ({}, {"start": 4, "stop": 100, "stride": 3}, {"start": 10}, {"stop": 7}, {"stride": 5}):
+        for fl in (None, feats, feats[::-1], feats[3:20:2]):
+            df = cio.create_dataframe_from_files([a, b], features_list=fl, file_label="traj_label", **kw)
+            lab = df.pop("traj_label").to_numpy()
+            X, names, labels = cio.create_matrix_from_sidecars([a, b], features_list=fl, chunk_rows=17, **kw)
+            assert names == df.columns.tolist()
+            assert X.dtype == np.float32 and np.array_equal(X, df.to_numpy(dtype=np.float32))
+            assert np.array_equal(labels, lab)
+    with pytest.raises(ValueError):
+        cio.create_matrix_from_sidecars([a], features_list=feats + ["nope"])
+    with pytest.raises(ValueError):
+        cio.create_matrix_from_sidecars([a], start=1000)
+    # preallocated (pinned-style) destination
+    buf = np.zeros((400, len(feats)), dtype=np.float32)
+    X, _, _ = cio.create_matrix_from_sidecars([a, b], features_list=feats, out=buf)
+    assert X.shape == (328, len(feats)) and np.shares_memory(X, buf)
+    # touching the text file invalidates the sidecar
+    with open(a, "a") as fh:
+        fh.write("\n")
+    assert not cio.has_fresh_sidecar(a) and cio.has_fresh_sidecar(b)
+
+
 def test_schemas_accept_reference_yaml_and_defaults():
     from deep_cartograph_b200.yaml_schemas.train_colvars import TrainColvarsSchema
     from deep_cartograph_b200.yaml_schemas.traj_cluster import TrajClusterSchema
