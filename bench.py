@@ -293,9 +293,9 @@ def main():
             if shards is None:
                 ops.kmeans_iterate_(P, C, labels, work, absmax=p_bound)   # one library call per Lloyd iteration
                 continue
-            r = ops.kmeans_step(P, C, labels, absmax=p_bound)
-            packed = shards.allreduce_sum_(torch.cat([r["sums"].reshape(-1), r["counts"]]))
-            ops.kmeans_update_(C, packed[:K * DIM].view(K, DIM), packed[K * DIM:])
+            r = ops.kmeans_step_packed_(P, C, labels, work, absmax=p_bound)      # [sums | counts | stats] in place
+            shards.allreduce_sum_(r["packed"])
+            ops.kmeans_update_(C, r["sums"], r["counts"], info=work[K * DIM + K + 3:K * DIM + K + 5])
       return evals, labels
 
     def sync_all():

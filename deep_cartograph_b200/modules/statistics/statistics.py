@@ -110,7 +110,7 @@ def kmeans_lloyd(Y: torch.Tensor, init_centers: torch.Tensor, max_iter: int = 30
     n_iter = 0
     res = None
     C = C.contiguous()
-    work = ops.kmeans_work(k, d, dev) if shards is None else None
+    work = ops.kmeans_work(k, d, dev)
     for it in range(max_iter):
         if shards is None:
             # single device: memset + E-step + FP64 sums + M-step finish in one library call
@@ -118,15 +118,14 @@ def kmeans_lloyd(Y: torch.Tensor, init_centers: torch.Tensor, max_iter: int = 30
             sums, counts = res["sums"], res["counts"]
             changed, _, _, n_empty, shift_tot = work[k * d + k:k * d + k + 5].tolist()   # ONE host read
         else:
-            res = ops.kmeans_step(Yc, C, labels, update_sums=True, want_gap=False, absmax=absmax)
-            packed = shards.allreduce_sum_(torch.cat([res["sums"].reshape(-1), res["counts"], res["stats"]]))
-            sums = packed[:k * d].view(k, d)
-            counts = packed[k * d:k * d + k]
-            stats = packed[k * d + k:]
+            # [sums | counts | stats] land in one buffer and are all-reduced in place
+            res = ops.kmeans_step_packed_(Yc, C, labels, work, absmax=absmax)
+            shards.allreduce_sum_(res["packed"])
+            sums, counts = res["sums"], res["counts"]
             # M-step finish on the device (centres updated in place unless a cluster is empty);
-            # ONE host read per iteration: [n_empty, shift, changed]
-            info = ops.kmeans_update_(C, sums.contiguous(), counts.contiguous())
-            n_empty, shift_tot, changed = torch.cat([info, stats[:1]]).tolist()
+            # ONE host read per iteration: [changed, inertia, ties, n_empty, shift]
+            ops.kmeans_update_(C, sums, counts, info=work[k * d + k + 3:k * d + k + 5])
+            changed, _, _, n_empty, shift_tot = work[k * d + k:k * d + k + 5].tolist()
         if n_empty > 0:
             empty = torch.nonzero(counts == 0).flatten()
             sums, counts = _relocate_empty(Yc, C, labels, sums, counts, empty, shards)

@@ -299,6 +299,35 @@ def kmeans_step(Y: torch.Tensor, centers: torch.Tensor, labels: torch.Tensor,
     return {"sums": sums, "counts": counts, "stats": stats, "gap": gap}
 
 
+_KM_WS = {}
+
+
+def kmeans_step_packed_(Y: torch.Tensor, centers: torch.Tensor, labels: torch.Tensor, work: torch.Tensor,
+                        absmax: Optional[torch.Tensor] = None) -> dict:
+    """E-step + M-step sums written into ONE buffer ``work = [sums k*d | counts k | stats 3 | ...]``
+    (``kmeans_work``): one memset, and a sharded Lloyd iteration can all-reduce ``work[:k*d + k + 3]``
+    in place without packing.  Returns views into ``work``."""
+    _need_cuda("Y", Y)
+    _need_cuda("centers", centers, torch.float64)
+    _need_cuda("labels", labels, torch.int32)
+    _need_cuda("work", work, torch.float64)
+    n, d, ld = _rows("Y", Y)
+    k = centers.shape[0]
+    if not centers.is_contiguous() or centers.shape[1] != d or work.numel() < k * d + k + 3:
+        raise ValueError("centers must be contiguous (k, d) and work at least k*d + k + 3 doubles")
+    ws = _KM_WS.get(Y.device)
+    if ws is None:
+        ws = _KM_WS[Y.device] = _ws(256, Y.device)
+    o = k * d
+    base = work.data_ptr()
+    _lib.call("dcg_kmeans_step", Y.data_ptr(), n, d, ld, _dtype_bytes(Y), centers.data_ptr(), k,
+              labels.data_ptr(), base, base + 8 * o, base + 8 * (o + k), None, 1,
+              _absmax_ptr(absmax, Y.device), ws.data_ptr(), ws.numel(), _stream())
+    _count(1)
+    return {"sums": work[:o].view(k, d), "counts": work[o:o + k], "stats": work[o + k:o + k + 3],
+            "packed": work[:o + k + 3]}
+
+
 def kmeans_update_(centers: torch.Tensor, sums: torch.Tensor, counts: torch.Tensor,
                    info: Optional[torch.Tensor] = None) -> torch.Tensor:
     """M-step finish on the device: ``info[0]`` = number of empty clusters; when there is none
@@ -346,9 +375,6 @@ def kmeans_iterate_(Y: torch.Tensor, centers: torch.Tensor, labels: torch.Tensor
     o = k * d
     return {"sums": work[:o].view(k, d), "counts": work[o:o + k], "stats": work[o + k:o + k + 3],
             "info": work[o + k + 3:o + k + 5]}
-
-
-_KM_WS = {}
 
 
 def nearest_to_centers(Y: torch.Tensor, centers: torch.Tensor) -> torch.Tensor:

@@ -130,9 +130,21 @@ def _kmeans_worker(rank, world, port, out):
                 C_new = sums * (1.0 / counts).unsqueeze(1)
                 shift = float(((C_new - C) ** 2).sum())
                 C.copy_(C_new)
-            return torch.tensor([float(n_empty), shift], dtype=torch.float64)
+            out_info = torch.tensor([float(n_empty), shift], dtype=torch.float64)
+            if info is not None:
+                info.copy_(out_info)
+                return info
+            return out_info
 
-        ops.kmeans_step, ops.kmeans_update_ = fake_step, fake_update
+        def fake_step_packed(Y, C, labels, work, absmax=None):
+            r = fake_step(Y, C, labels)
+            k, d = C.shape
+            o = k * d
+            work[:o] = r["sums"].reshape(-1); work[o:o + k] = r["counts"]; work[o + k:o + k + 3] = r["stats"]
+            return {"sums": work[:o].view(k, d), "counts": work[o:o + k], "stats": work[o + k:o + k + 3],
+                    "packed": work[:o + k + 3]}
+
+        ops.kmeans_step, ops.kmeans_update_, ops.kmeans_step_packed_ = fake_step, fake_update, fake_step_packed
         g = np.random.default_rng(3)
         k, d, n = 6, 3, 4001
         cent = g.uniform(-1, 1, size=(k, d))
