@@ -597,6 +597,76 @@ def test_kmeans_empty_cluster_relocation(dev):
     np.testing.assert_allclose(centers, res["centers"], rtol=1e-12, atol=1e-13)
 
 
+def test_kmeans_full_size_c5_properties(dev):
+    """BASELINE config C5, one GPU's share (12.5M frames x 10, k = 1000, float32) through
+    size-independent properties of a Lloyd E-step: every frame is counted once, the per-cluster sums
+    add up to the column sums, the reported inertia equals sum ||y - c_label||^2 recomputed in
+    float64 from the labels, no frame is closer (float64) to another centre on a strided sample, and
+    a second E-step with the same centres changes nothing (idempotence)."""
+    from deep_cartograph_b200 import ops
+    n, d, k = 12_500_000, 10, 1000
+    g = torch.Generator(device=dev).manual_seed(2)
+    cen = torch.rand((k, d), generator=g, device=dev) * 1.8 - 0.9
+    idx = torch.randint(0, k, (n,), generator=g, device=dev)
+    Y = (cen[idx] + 0.03 * torch.randn((n, d), generator=g, device=dev)).contiguous()
+    del idx
+    C = Y[:k].to(torch.float64).clone()                       # SURVEY 8d: fixed initial centroids = rows 0..999
+    bound = Y.abs().amax().to(torch.float64).reshape(1)
+    lab = torch.full((n,), -1, dtype=torch.int32, device=dev)
+    res = ops.kmeans_step(Y, C, lab, absmax=bound)
+    st = res["stats"].cpu().numpy()
+    assert st[0] == n
+    assert res["counts"].sum().item() == n and int(lab.min()) >= 0 and int(lab.max()) < k
+    colsum = Y.sum(dim=0, dtype=torch.float64)
+    tol = float(bound.item()) * n * 2.0 ** -40
+    assert (res["sums"].sum(dim=0) - colsum).abs().max().item() <= tol
+    inertia = 0.0
+    for s0 in range(0, n, 2_500_000):
+        yy = Y[s0:s0 + 2_500_000].double()
+        inertia += float(((yy - C[lab[s0:s0 + 2_500_000].long()]) ** 2).sum())
+    assert abs(st[1] - inertia) <= 1e-5 * inertia
+    samp = torch.arange(0, n, 997, device=dev)
+    D = torch.cdist(Y[samp].double(), C) ** 2
+    best = D.min(dim=1).values
+    mine = D.gather(1, lab[samp].long().unsqueeze(1)).squeeze(1)
+    assert (mine - best).max().item() <= 1e-12
+    res2 = ops.kmeans_step(Y, C, lab, absmax=bound)
+    assert res2["stats"].cpu().numpy()[0] == 0
+    assert torch.equal(res2["counts"], res["counts"])
+
+
+def test_projection_c3_shape_properties(dev):
+    """C3 feature count (4950, row stride 4952, five feature ranges) at 200k frames: the projection is
+    linear in W (P(W1 + W2) = P(W1) + P(W2) up to rounding), the block projection equals the dense
+    projection with the block-diagonal weights, and min / max are those of the output."""
+    from deep_cartograph_b200 import ops
+    n, f, d, ld = 200_000, 4950, 10, 4952
+    g = torch.Generator(device=dev).manual_seed(5)
+    buf = torch.full((n, ld), float("nan"), dtype=torch.float32, device=dev)
+    buf[:, :f] = torch.randn((n, f), generator=g, device=dev) * 0.3 + 2.0
+    X = buf[:, :f]
+    stt = ops.column_stats(X)
+    mean = stt["mean"].float()
+    rng = torch.sqrt(stt["m2"] / (n - 1)).float()
+    W1 = torch.randn((f, d), generator=g, device=dev) / f ** 0.5
+    W2 = torch.randn((f, d), generator=g, device=dev) / f ** 0.5
+    P1, _, _ = ops.project(X, W1, mean, rng, minmax=False)
+    P2, _, _ = ops.project(X, W2, mean, rng, minmax=False)
+    P12, pmin, pmax = ops.project(X, W1 + W2, mean, rng)
+    assert torch.isfinite(P12).all()
+    assert (P12 - (P1 + P2)).abs().max().item() <= 2e-5 * P12.abs().max().item()
+    assert torch.equal(pmin, P12.min(dim=0).values) and torch.equal(pmax, P12.max(dim=0).values)
+    block, s = 495, 5
+    Wc = torch.randn((f, s), generator=g, device=dev) / block ** 0.5
+    Pb = ops.project_blocks(X, Wc, block, mean, rng)
+    Wd = torch.zeros((f, 50), device=dev)
+    for b in range(10):
+        Wd[b * block:(b + 1) * block, b * s:(b + 1) * s] = Wc[b * block:(b + 1) * block]
+    Pd, _, _ = ops.project(X, Wd, mean, rng, minmax=False)
+    assert Pb.shape == Pd.shape == (n, 50)
+    assert (Pb - Pd).abs().max().item() <= 2e-5 * Pd.abs().max().item()
+
+
 # ------------------------------------------------------------------------------------------------
 # K3 nearest sample to each centre
 # ------------------------------------------------------------------------------------------------
