@@ -484,6 +484,31 @@ def test_kmeans_tensor_core_scan_labels_are_float64_argmin(dev, k, d, dt, scale)
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("engine", ["0", "1"])
+def test_kmeans_engines_agree(dev, monkeypatch, engine):
+    """DCG_KMEANS_TC selects the E-step engine (0: CUDA cores, 1: tcgen05 / TMEM scan, default:
+    register-resident mma.sync scan): all of them return the float64 arg-min labels and the same
+    counts; the sums agree to the fixed-point rounding."""
+    from deep_cartograph_b200 import ops
+    rng = np.random.default_rng(11)
+    k, d, n = 700, 10, 50001
+    cent = rng.uniform(-0.9, 0.9, size=(k, d))
+    Y = (cent[rng.integers(0, k, size=n)] + 0.03 * rng.standard_normal((n, d))).astype(np.float32)
+    Yd, Cd = _cuda(Y, dev), _cuda(Y[:k].astype(np.float64), dev)
+    bound = Yd.abs().amax().to(torch.float64).reshape(1)
+    lab_ref = torch.full((n,), -1, dtype=torch.int32, device=dev)
+    ref = ops.kmeans_step(Yd, Cd, lab_ref, absmax=bound)                  # default engine
+    monkeypatch.setenv("DCG_KMEANS_TC", engine)
+    lab = torch.full((n,), -1, dtype=torch.int32, device=dev)
+    res = ops.kmeans_step(Yd, Cd, lab, absmax=bound)
+    monkeypatch.delenv("DCG_KMEANS_TC")
+    assert torch.equal(lab, lab_ref)
+    assert torch.equal(res["counts"], ref["counts"])
+    np.testing.assert_allclose(res["sums"].cpu().numpy(), ref["sums"].cpu().numpy(), rtol=1e-11, atol=1e-9)
+    assert res["stats"][0].item() == n and res["stats"][2].item() == ref["stats"][2].item()
+
+
+@pytest.mark.gpu
 def test_kmeans_tensor_core_scan_counts_exact_ties(dev):
     """4-decimal CSV hand-off (reference traj_cluster_workflow.py:202): duplicated centres give exact
     ties, which the FP64 refine resolves to the lowest index and counts."""
