@@ -798,7 +798,7 @@ class DeepTICACalculator(CVCalculator):
             history = []
             for epoch in range(self.max_epochs):
                 model.train()
-                tot, nb = 0.0, 0
+                tot, nb = torch.zeros((), dtype=torch.float64, device=dev), 0      # no host read per minibatch
                 for b in self._epoch_batches(tr_idx, gen, self.shuffle):
                     if b.numel() <= d + 1:
                         continue
@@ -807,7 +807,7 @@ class DeepTICACalculator(CVCalculator):
                     loss.backward()
                     allreduce_gradients_(model.nn, sh)
                     opt.step()
-                    tot += float(loss.detach()); nb += 1
+                    tot += loss.detach(); nb += 1
                 if (epoch + 1) % self.check_val_every:
                     continue
                 model.eval()
@@ -819,7 +819,7 @@ class DeepTICACalculator(CVCalculator):
                         vl, _ = model.loss(X[b], X[b + lag], shards=sh)
                         vt += float(vl); vn += 1
                 last_val = vt / max(vn, 1)
-                history.append({"epoch": epoch + 1, "train_loss": tot / max(nb, 1), "valid_loss": last_val})
+                history.append({"epoch": epoch + 1, "train_loss": float(tot) / max(nb, 1), "valid_loss": last_val})
                 if last_val < best_val - self.min_delta:
                     best_val, bad = last_val, 0
                     best_state = {k: v.detach().clone() for k, v in model.state_dict().items()}

@@ -99,9 +99,58 @@ def reduced_eigenvalues(C0: torch.Tensor, Ct: torch.Tensor, reg: float) -> torch
     return torch.linalg.eigvalsh(A).flip(0)
 
 
+class _TicaLoss(torch.autograd.Function):
+    """(f, g, w, wl) -> (loss, eigenvalues) with the whole d x d part -- mean-free C0 / C_tau,
+    Cholesky reduction, eigenvalues, ``-sum lambda^2`` and dLoss/dC0, dLoss/dC_tau -- in ONE kernel
+    (``dcg_ticaloss_f64``) instead of ~40 tiny torch.linalg launches and their autograd backward.
+    The backward with respect to f and g is the analytic one of ``_TicaCov``."""
+
+    @staticmethod
+    def forward(ctx, f, g, w, wl, reg, n_eig, shards):
+        d = f.shape[1]
+        s = ops.ticacov_sums(f.detach(), g.detach(), w, wl)
+        if shards is not None:
+            shards.allreduce_sum_(s["flat"])
+        r = ops.ticaloss(s["flat"], d, reg, n_eig)
+        ctx.shards = shards
+        ctx.save_for_backward(f, g, w if w is not None else torch.empty(0, device=f.device),
+                              wl if wl is not None else torch.empty(0, device=f.device),
+                              r["mu"], r["sw"], r["swl"], r["G0"], r["Gt"])
+        ctx.mark_non_differentiable(r["evals"])
+        return r["loss"].clone(), r["evals"]
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_evals):
+        f, g, w, wl, mu, sw, swl, G0, Gt = ctx.saved_tensors
+        dt = f.dtype
+        B = f.shape[0]
+        wn = (w.to(torch.float64) / sw) if w.numel() else (torch.ones((), dtype=torch.float64, device=f.device) / sw).expand(B)
+        wln = (wl.to(torch.float64) / swl) if wl.numel() else (torch.ones((), dtype=torch.float64, device=f.device) / swl).expand(B)
+        ft = f.to(torch.float64) - mu
+        gt = g.to(torch.float64) - mu
+        # a batch whose C0 + reg I was not positive definite (NaN loss) contributes no gradient
+        H0 = torch.nan_to_num((G0 + G0.T) * g_loss, nan=0.0, posinf=0.0, neginf=0.0)
+        Ht = torch.nan_to_num((0.5 * g_loss) * (Gt + Gt.T), nan=0.0, posinf=0.0, neginf=0.0)
+        d_ft = wn[:, None] * (ft @ H0) + wln[:, None] * (gt @ Ht)
+        d_gt = wln[:, None] * (ft @ Ht)
+        tot = d_ft.sum(dim=0) + d_gt.sum(dim=0)
+        if ctx.shards is not None:
+            ctx.shards.allreduce_sum_(tot)
+        d_f = d_ft - wn[:, None] * tot
+        return d_f.to(dt), d_gt.to(dt), None, None, None, None, None
+
+
 def tica_loss(f: torch.Tensor, g: torch.Tensor, w: Optional[torch.Tensor] = None,
               wl: Optional[torch.Tensor] = None, reg: float = 1e-6, n_eig: int = 0, shards=None):
-    """DeepTICA loss ``-sum lambda_i^2`` and the eigenvalues (descending)."""
+    """DeepTICA loss ``-sum lambda_i^2`` and the eigenvalues (descending).  A batch whose
+    ``C0 + reg I`` is not positive definite gives a NaN loss (the reference's Cholesky raises)."""
+    return _TicaLoss.apply(f.contiguous(), g.contiguous(), w, wl, float(reg), int(n_eig or 0), shards)
+
+
+def tica_loss_reference(f: torch.Tensor, g: torch.Tensor, w: Optional[torch.Tensor] = None,
+                        wl: Optional[torch.Tensor] = None, reg: float = 1e-6, n_eig: int = 0, shards=None):
+    """The same loss through ``tica_covariances`` + torch.linalg autograd (validation of the fused
+    kernel; ~40 launches)."""
     C0, Ct = tica_covariances(f, g, w, wl, shards)
     evals = reduced_eigenvalues(C0, Ct, reg)
     used = evals[:n_eig] if n_eig and n_eig > 0 else evals

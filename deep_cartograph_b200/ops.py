@@ -419,3 +419,20 @@ def ticacov_sums(f: torch.Tensor, g: torch.Tensor, w: Optional[torch.Tensor] = N
     return {"flat": out, "sw": out[0], "swl": out[1], "swf": out[2:o],
             "sff": out[o:o + d * d].view(d, d), "sfg": out[o + d * d:o + 2 * d * d].view(d, d),
             "slf": out[o + 2 * d * d:o + 2 * d * d + d], "slg": out[o + 2 * d * d + d:]}
+
+
+def ticaloss(sums: torch.Tensor, d: int, reg: float, n_eig: int = 0) -> dict:
+    """DeepTICA eigen-loss and its gradient from the raw sums of ``ticacov_sums`` in one launch
+    (see dcg.h).  Returns dict(loss, status, sw, swl, evals, mu, G0, Gt) of views into one buffer."""
+    _need_cuda("sums", sums, torch.float64)
+    lib = _lib.load()
+    n_out = lib.dcg_ticaloss_out_doubles(d)
+    if n_out == 0 or sums.numel() < lib.dcg_ticacov_out_doubles(d) or not sums.is_contiguous():
+        raise ValueError("sums must be the contiguous output of ticacov_sums with 1 <= d <= 32")
+    res = torch.empty(n_out, dtype=torch.float64, device=sums.device)
+    _lib.call("dcg_ticaloss_f64", sums.data_ptr(), d, float(reg), int(n_eig), res.data_ptr(), _stream())
+    _count(1)
+    o = 4
+    return {"loss": res[0], "status": res[1], "sw": res[2], "swl": res[3], "evals": res[o:o + d],
+            "mu": res[o + d:o + 2 * d], "G0": res[o + 2 * d:o + 2 * d + d * d].view(d, d),
+            "Gt": res[o + 2 * d + d * d:].view(d, d)}

@@ -175,6 +175,18 @@ size_t dcg_ticacov_out_doubles(int d);
 int dcg_ticacov_f32(const float* f, const float* g, const float* w, const float* wl,
                     int64_t B, int d, double* out, void* stream);
 
+/* ---- A11: DeepTICA eigen-loss and its gradient ------------------------------------------------
+ * Replaces mlcolvar `cholesky_eigh` + `ReduceEigenvaluesLoss(mode='sum2')` and their autograd
+ * backward inside `DeepTICA.training_step` (driven from cv_calculator.py:1508-1524): from the raw
+ * sums of dcg_ticacov_f32 (after an all-reduce when the minibatch is sharded) one launch forms the
+ * mean-free symmetrised C0 / C_tau, B = C0 + reg I, L = chol(B), the eigenvalues of
+ * L^-1 C_tau L^-T (descending) and loss = -sum_{i < n_eig} lambda_i^2 (n_eig <= 0: all), together
+ * with dLoss/dC0 and dLoss/dC_tau (symmetric d x d).
+ * res (doubles): [0] loss, [1] status (0 ok, 1: B not positive definite, loss = NaN), [2] sum w,
+ * [3] sum wl, evals[d], mu[d] (weighted mean of f), G0[d*d], Gt[d*d].                            */
+size_t dcg_ticaloss_out_doubles(int d);
+int dcg_ticaloss_f64(const double* sums, int d, double reg, int n_eig, double* res, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

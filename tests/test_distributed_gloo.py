@@ -193,21 +193,6 @@ def test_shard_range_partitions_all_frames():
         assert all(rs[i][1] == rs[i + 1][0] for i in range(w - 1))
 
 
-def _cpu_ticacov_sums(f, g, w=None, wl=None):
-    """CPU stand-in for ops.ticacov_sums (the kernel's output layout, dcg.h)."""
-    f64, g64 = f.double(), g.double()
-    B, d = f.shape
-    w64 = torch.ones(B, dtype=torch.float64) if w is None else w.double()
-    wl64 = torch.ones(B, dtype=torch.float64) if wl is None else wl.double()
-    out = torch.cat([w64.sum().reshape(1), wl64.sum().reshape(1), (w64[:, None] * f64).sum(0),
-                     ((w64[:, None] * f64).T @ f64).reshape(-1), ((wl64[:, None] * f64).T @ g64).reshape(-1),
-                     (wl64[:, None] * f64).sum(0), (wl64[:, None] * g64).sum(0)])
-    o = 2 + d
-    return {"flat": out, "sw": out[0], "swl": out[1], "swf": out[2:o],
-            "sff": out[o:o + d * d].view(d, d), "sfg": out[o + d * d:o + 2 * d * d].view(d, d),
-            "slf": out[o + 2 * d * d:o + 2 * d * d + d], "slg": out[o + 2 * d * d + d:]}
-
-
 def _deeptica_worker(rank, world, port, out):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -217,8 +202,10 @@ def _deeptica_worker(rank, world, port, out):
         from deep_cartograph_b200 import ops
         from deep_cartograph_b200.modules.cv_learning import deep_tica
         from deep_cartograph_b200.parallel import FrameShards, shard_range
-        ops.ticacov_sums = _cpu_ticacov_sums
-        deep_tica.ops.ticacov_sums = _cpu_ticacov_sums
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from conftest import cpu_ticacov_sums, cpu_ticaloss
+        ops.ticacov_sums = cpu_ticacov_sums
+        ops.ticaloss = cpu_ticaloss
         torch.manual_seed(11)
         B, F, d = 301, 12, 3
         # slowly varying inputs so that C_tau is well conditioned
@@ -226,8 +213,9 @@ def _deeptica_worker(rank, world, port, out):
         x_t, x_lag = base[:B].float(), base[5:B + 5].float()
         net = torch.nn.Sequential(torch.nn.Linear(F, 8), torch.nn.Tanh(), torch.nn.Linear(8, d))
         ref = [p.detach().clone() for p in net.parameters()]
-        # single process: the whole minibatch
-        loss_all, ev_all = deep_tica.tica_loss(net(x_t), net(x_lag), reg=1e-6)
+        # single process, the whole minibatch, through torch.linalg autograd (independent of the
+        # analytic eigen-loss gradient used by tica_loss)
+        loss_all, ev_all = deep_tica.tica_loss_reference(net(x_t), net(x_lag), reg=1e-6)
         loss_all.backward()
         g_all = [p.grad.detach().clone() for p in net.parameters()]
         for p in net.parameters():

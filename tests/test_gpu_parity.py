@@ -763,6 +763,47 @@ def test_deeptica_loss_gradient_matches_torch_autograd(dev):
     np.testing.assert_allclose(g.grad.cpu().numpy(), g64.grad.cpu().numpy(), atol=2e-6 * g64.grad.abs().max().item() + 1e-9)
 
 
+@pytest.mark.parametrize("B,d,n_eig", [(4096, 2, 0), (8192, 4, 0), (8192, 10, 3), (4000, 32, 0), (1000, 1, 0)])
+def test_deeptica_fused_eigen_loss_matches_torch_linalg_autograd(dev, B, d, n_eig):
+    """dcg_ticaloss_f64 (Cholesky reduction + Jacobi eigenvalues + analytic gradient in one launch)
+    against the same loss through torch.linalg and autograd: loss, eigenvalues, df, dg."""
+    from deep_cartograph_b200.modules.cv_learning import deep_tica
+    g0 = torch.Generator(device=dev).manual_seed(B + d)
+    base = torch.randn((B, d), generator=g0, device=dev)
+    mix = torch.randn((d, d), generator=g0, device=dev) / d ** 0.5 + torch.eye(d, device=dev)
+    f = (base @ mix).requires_grad_(True)
+    rho = torch.linspace(0.95, 0.3, d, device=dev)
+    g = ((base * rho + torch.randn((B, d), generator=g0, device=dev) * torch.sqrt(1 - rho ** 2)) @ mix).requires_grad_(True)
+    w = torch.rand(B, generator=g0, device=dev) + 0.5
+    loss, ev = deep_tica.tica_loss(f, g, w, w, reg=1e-6, n_eig=n_eig)
+    loss.backward()
+    gf, gg = f.grad.clone(), g.grad.clone()
+    f.grad = None; g.grad = None
+    loss_r, ev_r = deep_tica.tica_loss_reference(f, g, w, w, reg=1e-6, n_eig=n_eig)
+    loss_r.backward()
+    assert abs(loss.item() - loss_r.item()) <= 1e-9 * max(1.0, abs(loss_r.item()))
+    np.testing.assert_allclose(ev.cpu().numpy(), ev_r.detach().cpu().numpy(), atol=1e-9)
+    sc = max(f.grad.abs().max().item(), g.grad.abs().max().item())
+    np.testing.assert_allclose(gf.cpu().numpy(), f.grad.cpu().numpy(), atol=2e-6 * sc + 1e-12)
+    np.testing.assert_allclose(gg.cpu().numpy(), g.grad.cpu().numpy(), atol=2e-6 * sc + 1e-12)
+
+
+def test_deeptica_fused_loss_flags_a_singular_batch(dev):
+    """C0 + reg I not positive definite (reg = 0, duplicated output column): NaN loss, status 1,
+    and a zero gradient instead of NaNs in the weights."""
+    from deep_cartograph_b200 import ops
+    from deep_cartograph_b200.modules.cv_learning import deep_tica
+    base = torch.randn((512, 1), device=dev)
+    f = torch.cat([base, base, -2 * base], dim=1).requires_grad_(True)       # rank 1
+    g = (f.detach() * 0.5).requires_grad_(True)
+    r = ops.ticaloss(ops.ticacov_sums(f.detach(), g.detach())["flat"], 3, -1e-3)
+    assert r["status"].item() == 1 and torch.isnan(r["loss"]).item()
+    loss, _ = deep_tica.tica_loss(f, g, reg=-1e-3)
+    loss.backward()
+    assert torch.isnan(loss).item()
+    assert torch.isfinite(f.grad).all() and f.grad.abs().max().item() == 0.0
+
+
 # ------------------------------------------------------------------------------------------------
 # calculators and step APIs on the C1 fixture (reference golden artefacts)
 # ------------------------------------------------------------------------------------------------

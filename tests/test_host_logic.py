@@ -434,22 +434,22 @@ def test_deeptica_covariance_backward_formula_cpu(monkeypatch):
     from deep_cartograph_b200 import ops
     from deep_cartograph_b200.modules.cv_learning import deep_tica
 
-    def fake_sums(f, g, w=None, wl=None):
-        f64, g64 = f.double(), g.double()
-        B = f.shape[0]
-        w64 = torch.ones(B, dtype=torch.float64) if w is None else w.double()
-        wl64 = torch.ones(B, dtype=torch.float64) if wl is None else wl.double()
-        return {"sw": w64.sum(), "swl": wl64.sum(), "swf": (w64[:, None] * f64).sum(0),
-                "sff": (w64[:, None] * f64).T @ f64, "sfg": (wl64[:, None] * f64).T @ g64,
-                "slf": (wl64[:, None] * f64).sum(0), "slg": (wl64[:, None] * g64).sum(0)}
-
-    monkeypatch.setattr(ops, "ticacov_sums", fake_sums)
+    from conftest import cpu_ticacov_sums, cpu_ticaloss
+    monkeypatch.setattr(ops, "ticacov_sums", cpu_ticacov_sums)
+    monkeypatch.setattr(ops, "ticaloss", cpu_ticaloss)
     torch.manual_seed(0)
     B, d = 300, 3
     f = torch.randn(B, d, requires_grad=True)
     g = (0.6 * f.detach() + 0.5 * torch.randn(B, d)).requires_grad_(True)
     w = torch.rand(B) + 0.5
+    # (i) covariance op + torch.linalg autograd, (ii) the fused eigen-loss with its analytic gradient
+    loss_r, evals_r = deep_tica.tica_loss_reference(f, g, w, w, reg=1e-6)
+    loss_r.backward()
+    gf_r, gg_r = f.grad.clone(), g.grad.clone()
+    f.grad = None; g.grad = None
     loss, evals = deep_tica.tica_loss(f, g, w, w, reg=1e-6)
+    assert abs(loss.item() - loss_r.item()) < 1e-10
+    np.testing.assert_allclose(evals.numpy(), evals_r.detach().numpy(), atol=1e-10)
     loss.backward()
     f2 = f.detach().double().requires_grad_(True)
     g2 = g.detach().double().requires_grad_(True)
@@ -467,3 +467,5 @@ def test_deeptica_covariance_backward_formula_cpu(monkeypatch):
     assert abs(loss.item() - rl) < 1e-9 and abs(ref.item() - rl) < 1e-9
     np.testing.assert_allclose(f.grad.numpy(), f2.grad.numpy(), atol=1e-6)
     np.testing.assert_allclose(g.grad.numpy(), g2.grad.numpy(), atol=1e-6)
+    np.testing.assert_allclose(gf_r.numpy(), f2.grad.numpy(), atol=1e-6)
+    np.testing.assert_allclose(gg_r.numpy(), g2.grad.numpy(), atol=1e-6)
