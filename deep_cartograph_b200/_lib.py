@@ -30,6 +30,7 @@ _SIGNATURES = {
     "dcg_colstats_workspace_bytes": (_c_sz, [_c_i64, _c_int]),
     "dcg_colstats_f32": (_c_int, [_p, _c_i64, _c_int, _c_i64, _p, _p, _p, _p, _p, _c_sz, _p]),
     "dcg_standardize_f32": (_c_int, [_p, _c_i64, _c_int, _c_i64, _p, _p, _p]),
+    "dcg_gather_standardize_f32": (_c_int, [_p, _c_i64, _c_int, _c_i64, _p, _c_i64, _c_i64, _p, _p, _p, _p]),
     "dcg_cov_workspace_bytes": (_c_sz, [_c_i64, _c_int, _c_int, _c_int, _c_int]),
     "dcg_cov_lag_f32": (_c_int, [_p, _c_i64, _c_int, _c_i64, _c_int, _p, _p, _c_int,
                                  _p, _p, _p, _p, _c_int, _p, _c_sz, _p]),

@@ -68,9 +68,62 @@ standardize_narrow_kernel(float* __restrict__ X, int64_t n, int f, int64_t ld,
   }
 }
 
+// DeepTICA minibatches (A11 / A12 feeder): Z[i, :] = (X[idx[i] + offset, :] - mean) / range in ONE
+// pass -- the reference gathers the batch, then `Normalization` (norm_in) subtracts and divides in
+// two more read+write passes over B x F (mlcolvar Normalization.forward, model built at
+// cv_calculator.py:2569-2590).  A warp owns a row at a time; the column parameters of a lane's
+// vectors are re-read from L1 (rows are random, so there is nothing to keep in registers across
+// rows beyond one vector).
+template <int VEC>
+__global__ void __launch_bounds__(256)
+gather_standardize_kernel(const float* __restrict__ X, int f, int64_t ld, const int64_t* __restrict__ idx,
+                          int64_t nb, int64_t offset, const float* __restrict__ mean,
+                          const float* __restrict__ range, float* __restrict__ Z) {
+  using V = typename VecT<VEC>::type;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp0; i < nb; i += nwarps) {
+    const float* src = X + (idx[i] + offset) * ld;
+    float* dst = Z + i * (int64_t)f;
+    int col = lane * VEC;
+    for (; col + VEC <= f; col += 32 * VEC) {
+      V x = *reinterpret_cast<const V*>(src + col);
+      float* e = reinterpret_cast<float*>(&x);
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        const float r = __ldg(range + col + v);
+        e[v] = standardize1(e[v], __ldg(mean + col + v), r, 1.0f / r);
+      }
+      *reinterpret_cast<V*>(dst + col) = x;
+    }
+    for (int c = col; c < f && c < col + VEC; ++c) {          // partial last vector
+      const float r = __ldg(range + c);
+      dst[c] = standardize1(src[c], __ldg(mean + c), r, 1.0f / r);
+    }
+  }
+}
+
 }  // namespace dcg
 
 using namespace dcg;
+
+extern "C" int dcg_gather_standardize_f32(const float* X, int64_t n, int f, int64_t ld,
+                                          const int64_t* idx, int64_t nb, int64_t offset,
+                                          const float* mean, const float* range, float* Z, void* stream) {
+  if (!X || !idx || !mean || !range || !Z) return DCG_E_NULL;
+  if (n <= 0 || f <= 0 || ld < f || nb <= 0 || offset < 0 || offset >= n) return DCG_E_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  // source rows: ld-strided (vector width from X / ld); destination rows are f floats apart
+  int vec = row_vec_width(X, ld);
+  while (vec > 1 && (f % vec || (uintptr_t)Z % (4 * vec))) vec >>= 1;
+  const int64_t blocks = std::min<int64_t>(ceil_div(nb, 8), (int64_t)kNumSMs * 8);
+  if (vec == 4) gather_standardize_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(X, f, ld, idx, nb, offset, mean, range, Z);
+  else if (vec == 2) gather_standardize_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(X, f, ld, idx, nb, offset, mean, range, Z);
+  else gather_standardize_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(X, f, ld, idx, nb, offset, mean, range, Z);
+  DCG_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" int dcg_standardize_f32(float* X, int64_t n, int f, int64_t ld,
                                    const float* mean, const float* range, void* stream) {

@@ -802,7 +802,7 @@ class DeepTICACalculator(CVCalculator):
                 for b in self._epoch_batches(tr_idx, gen, self.shuffle):
                     if b.numel() <= d + 1:
                         continue
-                    loss, _ = model.loss(X[b], X[b + lag], shards=sh)
+                    loss, _ = model.loss_indexed(X, b, lag, shards=sh)
                     opt.zero_grad(set_to_none=True)
                     loss.backward()
                     allreduce_gradients_(model.nn, sh)
@@ -816,7 +816,7 @@ class DeepTICACalculator(CVCalculator):
                     for b in self._epoch_batches(va_idx, gen, False):
                         if b.numel() <= d + 1:
                             continue
-                        vl, _ = model.loss(X[b], X[b + lag], shards=sh)
+                        vl, _ = model.loss_indexed(X, b, lag, shards=sh)
                         vt += float(vl); vn += 1
                 last_val = vt / max(vn, 1)
                 history.append({"epoch": epoch + 1, "train_loss": float(tot) / max(nb, 1), "valid_loss": last_val})
@@ -830,7 +830,7 @@ class DeepTICACalculator(CVCalculator):
             if last_val is None:                             # never validated: validate once
                 model.eval()
                 with torch.no_grad():
-                    last_val = float(model.loss(X[va_idx], X[va_idx + lag], shards=sh)[0]) if va_idx.numel() > d + 1 else float("nan")
+                    last_val = float(model.loss_indexed(X, va_idx, lag, shards=sh)[0]) if va_idx.numel() > d + 1 else float("nan")
                 best_val = last_val
             score = best_val if self.model_to_save == "best" else last_val
             ok = bool(np.isfinite(score)) and score >= -float(d) - 1e-6      # reference :1624-1626

@@ -191,6 +191,13 @@ class DeepTICA(nn.Module):
     def loss(self, x_t: torch.Tensor, x_lag: torch.Tensor, w=None, wl=None, shards=None):
         return tica_loss(self.features(x_t), self.features(x_lag), w, wl, reg=self.reg, shards=shards)
 
+    def loss_indexed(self, X: torch.Tensor, idx: torch.Tensor, lag: int, w=None, wl=None, shards=None):
+        """``loss(X[idx], X[idx + lag])`` with the two minibatches gathered and passed through
+        ``norm_in`` by one kernel each (same float32 values as ``features``)."""
+        z_t = ops.gather_standardize(X, idx, self.in_mean, self.in_range, 0)
+        z_l = ops.gather_standardize(X, idx, self.in_mean, self.in_range, lag)
+        return tica_loss(self.nn(z_t), self.nn(z_l), w, wl, reg=self.reg, shards=shards)
+
     @torch.no_grad()
     def fit_tica_layer(self, x_t: torch.Tensor, x_lag: torch.Tensor):
         """Freeze the linear TICA read-out from the current network outputs (unit-L2 columns,

@@ -436,3 +436,23 @@ def ticaloss(sums: torch.Tensor, d: int, reg: float, n_eig: int = 0) -> dict:
     return {"loss": res[0], "status": res[1], "sw": res[2], "swl": res[3], "evals": res[o:o + d],
             "mu": res[o + d:o + 2 * d], "G0": res[o + 2 * d:o + 2 * d + d * d].view(d, d),
             "Gt": res[o + 2 * d + d * d:].view(d, d)}
+
+
+def gather_standardize(X: torch.Tensor, idx: torch.Tensor, mean: torch.Tensor, rng: torch.Tensor,
+                       offset: int = 0) -> torch.Tensor:
+    """``(X[idx + offset] - mean) / range`` (a DeepTICA minibatch through ``norm_in``) in one pass.
+    ``idx`` is an int64 CUDA tensor of row indices with ``0 <= idx + offset < X.shape[0]``."""
+    _need_cuda("X", X, torch.float32)
+    _need_cuda("idx", idx, torch.int64)
+    _need_cuda("mean", mean, torch.float32)
+    _need_cuda("range", rng, torch.float32)
+    n, f, ld = _rows("X", X)
+    idx = idx.contiguous()
+    nb = idx.numel()
+    Z = torch.empty((nb, f), dtype=torch.float32, device=X.device)
+    if nb == 0:
+        return Z
+    _lib.call("dcg_gather_standardize_f32", X.data_ptr(), n, f, ld, idx.data_ptr(), nb, int(offset),
+              mean.contiguous().data_ptr(), rng.contiguous().data_ptr(), Z.data_ptr(), _stream())
+    _count(1)
+    return Z

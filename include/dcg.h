@@ -66,6 +66,16 @@ int dcg_colstats_f32(const float* X, int64_t n, int f, int64_t ld,
 int dcg_standardize_f32(float* X, int64_t n, int f, int64_t ld,
                         const float* mean, const float* range, void* stream);
 
+/* ---- A11/A12 feeder: gathered, standardised minibatch ------------------------------------------
+ * Z[i, :] = (X[idx[i] + offset, :] - mean) / range for i < nb (IEEE float32 subtraction and
+ * division, as mlcolvar `Normalization.forward`, the `norm_in` layer of the DeepTICA model built at
+ * cv_calculator.py:2569-2590) in one pass instead of a gather and two read+write passes.  idx is
+ * int64 (device), every idx[i] + offset must lie in [0, n) (not checked); Z is nb x f, row-major,
+ * contiguous.                                                                                    */
+int dcg_gather_standardize_f32(const float* X, int64_t n, int f, int64_t ld,
+                               const int64_t* idx, int64_t nb, int64_t offset,
+                               const float* mean, const float* range, float* Z, void* stream);
+
 /* ---- A5/A6/A7/A8: fused standardise + C0 / C_tau accumulation -------------------------------
  * Replaces mlcolvar `create_timelagged_dataset` + `TICA.compute`'s correlation sums
  * (cv_calculator.py:2244-2261, 2306-2378) and sklearn PCA's Gram (cv_calculator.py:2204-2210).

@@ -788,6 +788,38 @@ def test_deeptica_fused_eigen_loss_matches_torch_linalg_autograd(dev, B, d, n_ei
     np.testing.assert_allclose(gg.cpu().numpy(), g.grad.cpu().numpy(), atol=2e-6 * sc + 1e-12)
 
 
+@pytest.mark.parametrize("n,f,ld,nb,off", [(5000, 1000, 1000, 4096, 10), (3000, 54, 56, 999, 1), (2000, 33, 33, 517, 0),
+                                           (1500, 4950, 4952, 300, 7)])
+def test_gather_standardize_is_bitwise_norm_in(dev, n, f, ld, nb, off):
+    """The fused minibatch gather + `norm_in` equals torch's `(X[idx + off] - mean) / range` bit for
+    bit (IEEE float32 subtraction and division), for aligned, padded and odd row strides."""
+    from deep_cartograph_b200 import ops
+    g0 = torch.Generator(device=dev).manual_seed(n + f)
+    buf = torch.full((n, ld), float("nan"), dtype=torch.float32, device=dev)
+    buf[:, :f] = torch.randn((n, f), generator=g0, device=dev) * 0.3 + 2.0
+    X = buf[:, :f]
+    mean = X.mean(0)
+    rng = X.std(0) * (0.5 + torch.rand(f, generator=g0, device=dev))
+    idx = torch.randint(0, n - off, (nb,), generator=g0, device=dev)
+    Z = ops.gather_standardize(X, idx, mean, rng, off)
+    ref = (X[idx + off] - mean) / rng
+    assert Z.shape == ref.shape and torch.equal(Z, ref)
+
+
+def test_deeptica_indexed_loss_equals_gathered_loss(dev):
+    from deep_cartograph_b200.modules.cv_learning.deep_tica import DeepTICA
+    torch.manual_seed(3)
+    n, f, d, lag = 20000, 64, 3, 5
+    X = torch.cumsum(torch.randn((n, f), device=dev), dim=0) * 0.05 + torch.randn((n, f), device=dev)
+    model = DeepTICA([f, 16, d], X.mean(0), X.std(0), activation="tanh").to(dev)
+    idx = torch.randint(0, n - lag, (4096,), device=dev)
+    l1, e1 = model.loss(X[idx], X[idx + lag])
+    l2, e2 = model.loss_indexed(X, idx, lag)
+    assert torch.equal(l1, l2) and torch.equal(e1, e2)
+    l2.backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.nn.parameters())
+
+
 def test_deeptica_fused_loss_flags_a_singular_batch(dev):
     """C0 + reg I not positive definite (reg = 0, duplicated output column): NaN loss, status 1,
     and a zero gradient instead of NaNs in the weights."""

@@ -27,7 +27,7 @@ g = torch.Generator(device=dev).manual_seed(0)
 
 def step():
     idx = torch.randint(0, n - lag, (B,), generator=g, device=dev)
-    loss, ev = model.loss(X[idx], X[idx + lag])
+    loss, ev = model.loss_indexed(X, idx, lag)
     opt.zero_grad(set_to_none=True)
     loss.backward()
     opt.step()
