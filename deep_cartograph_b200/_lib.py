@@ -50,6 +50,7 @@ _SIGNATURES = {
                                         _p, _c_sz, _p]),
     "dcg_ticacov_out_doubles": (_c_sz, [_c_int]),
     "dcg_ticacov_f32": (_c_int, [_p, _p, _p, _p, _c_i64, _c_int, _p, _p]),
+    "dcg_gen_eig_small_f64": (_c_int, [_p, _p, _c_int, _c_int, _p, _p, _p, _p]),
     "dcg_ticaloss_out_doubles": (_c_sz, [_c_int]),
     "dcg_ticaloss_f64": (_c_int, [_p, _c_int, C.c_double, _c_int, _p, _p]),
 }

@@ -270,9 +270,146 @@ ticaloss_kernel(const double* __restrict__ sums, int d, double reg, int n_eig, d
   }
 }
 
+// ---- small generalised symmetric eigenproblem  H s = theta G s  (b <= 32, G SPD), batched ---------
+// The Rayleigh-Ritz step of the shift-and-invert eigen stage (linalg.py) and of any other small
+// pencil: Cholesky of G, A = L^-1 H L^-T, cyclic Jacobi, S = L^-T U with the eigenvalues in
+// DESCENDING order -- one launch per batch instead of cholesky_ex + solve_triangular + two GEMMs +
+// eigh (whose error check is a host synchronisation) + flips.  One warp per pencil.
+__global__ void __launch_bounds__(32)
+gen_eig_small_kernel(const double* __restrict__ Hm, const double* __restrict__ Gm, int b,
+                     double* __restrict__ theta, double* __restrict__ Sm, double* __restrict__ status) {
+  __shared__ double G[32][33], H[32][33], L[32][33], A[32][33], V[32][33];
+  __shared__ int order[32];
+  __shared__ int s_bad;
+  const int lane = threadIdx.x;
+  const size_t base = (size_t)blockIdx.x * b * b;
+  double (*Li)[33] = G;                                  // G is dead once factorised
+  if (lane == 0) s_bad = 0;
+  if (lane < b)
+    for (int j = 0; j < b; ++j) {
+      G[lane][j] = 0.5 * (Gm[base + lane * b + j] + Gm[base + j * b + lane]);
+      H[lane][j] = 0.5 * (Hm[base + lane * b + j] + Hm[base + j * b + lane]);
+    }
+  __syncwarp();
+  for (int j = 0; j < b; ++j) {
+    if (lane == j) {
+      double s = G[j][j];
+      for (int k = 0; k < j; ++k) s -= L[j][k] * L[j][k];
+      if (!(s > 0.0)) { s_bad = 1; s = 1.0; }
+      L[j][j] = sqrt(s);
+    }
+    __syncwarp();
+    if (lane > j && lane < b) {
+      double s = G[lane][j];
+      for (int k = 0; k < j; ++k) s -= L[lane][k] * L[j][k];
+      L[lane][j] = s / L[j][j];
+    }
+    if (lane < j) L[lane][j] = 0.0;
+    __syncwarp();
+  }
+  if (lane < b) {
+    const int c = lane;
+    for (int i = 0; i < b; ++i) {
+      double s = (i == c) ? 1.0 : 0.0;
+      for (int k = c; k < i; ++k) s -= L[i][k] * Li[k][c];
+      Li[i][c] = (i < c) ? 0.0 : s / L[i][i];
+    }
+  }
+  __syncwarp();
+  if (lane < b)
+    for (int j = 0; j < b; ++j) {
+      double s = 0.0;
+      for (int k = 0; k <= lane; ++k) s += Li[lane][k] * H[k][j];
+      V[lane][j] = s;
+    }
+  __syncwarp();
+  if (lane < b)
+    for (int j = 0; j < b; ++j) {
+      double s = 0.0;
+      for (int k = 0; k <= j; ++k) s += V[lane][k] * Li[j][k];
+      A[lane][j] = s;
+    }
+  __syncwarp();
+  if (lane < b)
+    for (int j = lane + 1; j < b; ++j) A[lane][j] = 0.5 * (A[lane][j] + A[j][lane]);
+  __syncwarp();
+  if (lane < b) {
+    for (int j = 0; j < lane; ++j) A[lane][j] = A[j][lane];
+    for (int j = 0; j < b; ++j) V[lane][j] = (lane == j) ? 1.0 : 0.0;
+  }
+  __syncwarp();
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    double off = 0.0, diag = 0.0;
+    if (lane < b) {
+      for (int j = 0; j < b; ++j) { if (j != lane) off += A[lane][j] * A[lane][j]; }
+      diag = A[lane][lane] * A[lane][lane];
+    }
+    off = warp_sum(off);
+    diag = warp_sum(diag);
+    if (off <= 1e-32 * diag || off == 0.0) break;
+    for (int p = 0; p < b - 1; ++p)
+      for (int q = p + 1; q < b; ++q) {
+        const double apq = A[p][q];
+        if (apq != 0.0) {
+          const double app = A[p][p], aqq = A[q][q];
+          const double th = (aqq - app) / (2.0 * apq);
+          const double t = (th >= 0.0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));
+          const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+          __syncwarp();
+          if (lane < b) {
+            const int k = lane;
+            if (k != p && k != q) {
+              const double akp = A[k][p], akq = A[k][q];
+              const double np_ = c * akp - sn * akq, nq_ = sn * akp + c * akq;
+              A[k][p] = np_; A[p][k] = np_;
+              A[k][q] = nq_; A[q][k] = nq_;
+            }
+            const double vkp = V[k][p], vkq = V[k][q];
+            V[k][p] = c * vkp - sn * vkq;
+            V[k][q] = sn * vkp + c * vkq;
+          }
+          if (lane == 0) {
+            A[p][p] = app - t * apq;
+            A[q][q] = aqq + t * apq;
+            A[p][q] = 0.0; A[q][p] = 0.0;
+          }
+          __syncwarp();
+        }
+      }
+  }
+  if (lane < b) {
+    const double mine = A[lane][lane];
+    int r = 0;
+    for (int j = 0; j < b; ++j) {
+      const double o = A[j][j];
+      r += (o > mine) || (o == mine && j < lane);
+    }
+    order[r] = lane;
+    theta[(size_t)blockIdx.x * b + r] = mine;
+  }
+  __syncwarp();
+  if (lane < b)
+    for (int r = 0; r < b; ++r) {
+      const int col = order[r];
+      double s = 0.0;
+      for (int k = lane; k < b; ++k) s += Li[k][lane] * V[k][col];
+      Sm[base + lane * b + r] = s;
+    }
+  if (lane == 0) status[blockIdx.x] = (double)s_bad;
+}
+
 }  // namespace dcg
 
 using namespace dcg;
+
+extern "C" int dcg_gen_eig_small_f64(const double* H, const double* G, int b, int batch,
+                                     double* theta, double* S, double* status, void* stream) {
+  if (!H || !G || !theta || !S || !status) return DCG_E_NULL;
+  if (b < 1 || b > 32 || batch < 1) return DCG_E_SHAPE;
+  gen_eig_small_kernel<<<batch, 32, 0, (cudaStream_t)stream>>>(H, G, b, theta, S, status);
+  DCG_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" size_t dcg_ticaloss_out_doubles(int d) {
   if (d < 1 || d > 32) return 0;

@@ -105,20 +105,28 @@ def _shift_invert_topk(B: torch.Tensor, Ct: torch.Tensor, out: int, tol: float =
         BX = B @ X
         CX = Ct @ X
         Gb = X.mT @ BX
-        Lb, info = torch.linalg.cholesky_ex(0.5 * (Gb + Gb.mT))
-        if int(info.abs().max().item()) != 0:
-            return None
-        Lbi = torch.linalg.solve_triangular(Lb, eye_b.expand(nb, b, b), upper=False)
-        Hs = Lbi @ (X.mT @ CX) @ Lbi.mT
-        theta, S = torch.linalg.eigh(0.5 * (Hs + Hs.mT))
-        theta = theta.flip(-1)
-        S = Lbi.mT @ S.flip(-1)
+        if X.is_cuda and b <= 32:
+            # the b x b pencil in one launch (Cholesky + Jacobi), its status rides on the host read below
+            from . import ops
+            theta, S, bad = ops.gen_eig_small(X.mT @ CX, Gb)
+        else:
+            Lb, info = torch.linalg.cholesky_ex(0.5 * (Gb + Gb.mT))
+            if int(info.abs().max().item()) != 0:
+                return None
+            Lbi = torch.linalg.solve_triangular(Lb, eye_b.expand(nb, b, b), upper=False)
+            Hs = Lbi @ (X.mT @ CX) @ Lbi.mT
+            theta, S = torch.linalg.eigh(0.5 * (Hs + Hs.mT))
+            theta = theta.flip(-1)
+            S = Lbi.mT @ S.flip(-1)
+            bad = torch.zeros(nb, dtype=B.dtype, device=B.device)
         X = X @ S
         res = torch.linalg.norm(CX @ S[..., :out] - (BX @ S[..., :out]) * theta[:, None, :out], dim=-2)
         rel = res / (nrm * torch.linalg.norm(X[..., :out], dim=-2))
         # one host read per round: worst residual + the Ritz values the shift logic needs
         host = torch.cat([rel.max().reshape(1), theta[:, 0], theta[:, out - 1], theta[:, b - 1],
-                          sigma.reshape(-1)]).tolist()
+                          sigma.reshape(-1), bad.max().reshape(1)]).tolist()
+        if host[-1] != 0:
+            return None
         worst = host[0]
         if worst <= tol:
             EIG_STATS["fast"] += nb

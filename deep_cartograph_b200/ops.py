@@ -456,3 +456,23 @@ def gather_standardize(X: torch.Tensor, idx: torch.Tensor, mean: torch.Tensor, r
               mean.contiguous().data_ptr(), rng.contiguous().data_ptr(), Z.data_ptr(), _stream())
     _count(1)
     return Z
+
+
+def gen_eig_small(H: torch.Tensor, G: torch.Tensor):
+    """``H s = theta G s`` for a batch of b x b pencils (b <= 32, FP64, G SPD) in one launch:
+    returns (theta (nb, b) descending, S (nb, b, b) with G-orthonormal eigenvector columns,
+    status (nb,) -- 0 ok, 1 where G was not positive definite).  Nothing is synchronised."""
+    _need_cuda("H", H, torch.float64)
+    _need_cuda("G", G, torch.float64)
+    if H.dim() != 3 or H.shape != G.shape or H.shape[-1] != H.shape[-2] or H.shape[-1] > 32:
+        raise ValueError("H and G must be (batch, b, b) with b <= 32")
+    nb, b = H.shape[0], H.shape[-1]
+    H = H.contiguous()
+    G = G.contiguous()
+    theta = torch.empty((nb, b), dtype=torch.float64, device=H.device)
+    S = torch.empty((nb, b, b), dtype=torch.float64, device=H.device)
+    status = torch.empty(nb, dtype=torch.float64, device=H.device)
+    _lib.call("dcg_gen_eig_small_f64", H.data_ptr(), G.data_ptr(), b, nb, theta.data_ptr(), S.data_ptr(),
+              status.data_ptr(), _stream())
+    _count(1)
+    return theta, S, status

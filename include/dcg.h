@@ -197,6 +197,16 @@ int dcg_ticacov_f32(const float* f, const float* g, const float* w, const float*
 size_t dcg_ticaloss_out_doubles(int d);
 int dcg_ticaloss_f64(const double* sums, int d, double reg, int n_eig, double* res, void* stream);
 
+/* ---- eigen stage: small generalised symmetric eigenproblem -------------------------------------
+ * H s = theta G s for `batch` independent b x b pencils (b <= 32, G symmetric positive definite,
+ * row-major FP64; only the symmetric parts are used): theta[batch][b] DESCENDING, S[batch][b][b]
+ * with the G-orthonormal eigenvectors as columns in the same order, status[batch] (0 ok, 1: G not
+ * positive definite).  The Rayleigh-Ritz step of the top-d solver that stands in for mlcolvar
+ * `cholesky_eigh` as called from TICA.compute (cv_calculator.py:2257-2261): one launch instead of
+ * cholesky_ex + solve_triangular + GEMMs + eigh (whose error check synchronises the host).        */
+int dcg_gen_eig_small_f64(const double* H, const double* G, int b, int batch,
+                          double* theta, double* S, double* status, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

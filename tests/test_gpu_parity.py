@@ -836,6 +836,30 @@ def test_deeptica_fused_loss_flags_a_singular_batch(dev):
     assert torch.isfinite(f.grad).all() and f.grad.abs().max().item() == 0.0
 
 
+@pytest.mark.parametrize("b,nb", [(12, 1), (13, 10), (32, 3), (1, 2), (5, 7)])
+def test_small_generalised_eigenproblem_kernel(dev, b, nb):
+    """dcg_gen_eig_small_f64 (Cholesky + cyclic Jacobi, one warp per pencil) against torch.linalg:
+    eigenvalues descending, H S = G S diag(theta), S^T G S = I; an indefinite G is flagged."""
+    from deep_cartograph_b200 import ops
+    g0 = torch.Generator(device=dev).manual_seed(b * 10 + nb)
+    R = torch.randn((nb, b, b + 3), generator=g0, device=dev, dtype=torch.float64)
+    G = R @ R.mT + 0.1 * torch.eye(b, device=dev, dtype=torch.float64)
+    Q = torch.randn((nb, b, b), generator=g0, device=dev, dtype=torch.float64)
+    H = 0.5 * (Q + Q.mT)
+    theta, S, status = ops.gen_eig_small(H, G)
+    assert (status == 0).all()
+    L = torch.linalg.cholesky(G)
+    Li = torch.linalg.inv(L)
+    ref = torch.linalg.eigvalsh(Li @ H @ Li.mT).flip(-1)
+    np.testing.assert_allclose(theta.cpu().numpy(), ref.cpu().numpy(), rtol=1e-11, atol=1e-12)
+    assert (H @ S - (G @ S) * theta[:, None, :]).abs().max().item() < 1e-10 * H.abs().max().item() * max(1.0, S.abs().max().item())
+    eye = torch.eye(b, device=dev, dtype=torch.float64)
+    assert (S.mT @ G @ S - eye).abs().max().item() < 1e-11
+    Gbad = G.clone(); Gbad[0] = -Gbad[0]
+    _, _, st2 = ops.gen_eig_small(H, Gbad)
+    assert st2[0].item() == 1 and (st2[1:] == 0).all()
+
+
 # ------------------------------------------------------------------------------------------------
 # calculators and step APIs on the C1 fixture (reference golden artefacts)
 # ------------------------------------------------------------------------------------------------
