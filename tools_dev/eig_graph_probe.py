@@ -43,11 +43,7 @@ def fixed(Bm, Cm):
             Xc = torch.linalg.solve_triangular(Lg.mT, Xc, upper=True, left=False)
     BX = Bm @ Xc; CX = Cm @ Xc
     Gb = Xc.mT @ BX
-    Lb, info2 = torch.linalg.cholesky_ex(0.5 * (Gb + Gb.mT))
-    Lbi = torch.linalg.solve_triangular(Lb, eye_b.expand(1, b, b), upper=False)
-    Hs = Lbi @ (Xc.mT @ CX) @ Lbi.mT
-    theta, S = torch.linalg.eigh(0.5 * (Hs + Hs.mT))
-    theta = theta.flip(-1); S = Lbi.mT @ S.flip(-1)
+    theta, S, info2 = ops.gen_eig_small(Xc.mT @ CX, Gb)
     Xr = Xc @ S
     res = torch.linalg.norm(CX @ S[..., :out] - (BX @ S[..., :out]) * theta[:, None, :out], dim=-2)
     rel = res / (nrm * torch.linalg.norm(Xr[..., :out], dim=-2))
