@@ -156,14 +156,19 @@ class CVCalculator:
             # binary sidecars: memory-mapped float32 tables, no text parsing, gathered
             # straight into a pinned buffer that load_training_tensor streams to the device
             logger.info("Reading training data from binary colvars sidecars...")
-            Xh, names, labels = colvars_io.create_matrix_from_sidecars(paths, features_list=features_list,
-                                                                       **self.training_reading_settings)
-            X = torch.from_numpy(Xh)
-            if torch.cuda.is_available():
+            holder = {}
+
+            def pinned(rows, feats):
                 try:
-                    X = X.pin_memory()
+                    holder["t"] = torch.empty((rows, feats), dtype=torch.float32, pin_memory=torch.cuda.is_available())
                 except RuntimeError:
-                    pass
+                    holder["t"] = torch.empty((rows, feats), dtype=torch.float32)
+                return holder["t"].numpy()
+
+            Xh, names, labels = colvars_io.create_matrix_from_sidecars(paths, features_list=features_list,
+                                                                       allocator=pinned,
+                                                                       **self.training_reading_settings)
+            X = holder["t"][:Xh.shape[0]]
             self.load_training_tensor(X, names, labels)
             return
         logger.info("Reading training data from colvars files...")

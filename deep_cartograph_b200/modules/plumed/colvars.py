@@ -131,12 +131,13 @@ def create_matrix_from_sidecars(colvars_paths: Union[List[str], str],
                                 features_list: Optional[List[str]] = None,
                                 start: int = 0, stop: Optional[int] = None, stride: int = 1,
                                 out: Optional[np.ndarray] = None, chunk_rows: int = 1 << 16,
-                                **_ignored) -> Tuple[np.ndarray, List[str], np.ndarray]:
+                                allocator=None, **_ignored) -> Tuple[np.ndarray, List[str], np.ndarray]:
     """Same result as `create_dataframe_from_files(..., file_label='traj_label')` -- per-file
     `[start:stop:stride]`, drop of time / labels / bias / walker columns, `features_list` selects and
     orders, files concatenated in order -- as (float32 matrix, column names, file index per row),
     gathered from the memory-mapped sidecars in row chunks.  `out` may be a preallocated (e.g.
-    pinned) buffer of at least the result's shape."""
+    pinned) buffer of at least the result's shape; `allocator(rows, features)` may provide one once
+    the shape is known (the calculators allocate pinned memory this way: no second host copy)."""
     if isinstance(colvars_paths, str):
         colvars_paths = [colvars_paths]
     plans = []
@@ -162,6 +163,8 @@ def create_matrix_from_sidecars(colvars_paths: Union[List[str], str],
     if total == 0:
         raise ValueError("The resulting dataframe is empty.")
     f = len(names_ref)
+    if out is None and allocator is not None:
+        out = allocator(total, f)
     if out is None:
         out = np.empty((total, f), dtype=np.float32)
     elif out.shape[0] < total or out.shape[1] != f or out.dtype != np.float32:

@@ -285,6 +285,14 @@ def test_binary_sidecar_matches_text_reader(tmp_path):
     buf = np.zeros((400, len(feats)), dtype=np.float32)
     X, _, _ = cio.create_matrix_from_sidecars([a, b], features_list=feats, out=buf)
     assert X.shape == (328, len(feats)) and np.shares_memory(X, buf)
+    got = {}
+
+    def alloc(rows, feats):
+        got["buf"] = np.full((rows, feats), -1.0, dtype=np.float32)
+        return got["buf"]
+
+    X2, _, _ = cio.create_matrix_from_sidecars([a, b], features_list=feats, allocator=alloc)
+    assert np.shares_memory(X2, got["buf"]) and np.array_equal(X2, X)
     # touching the text file invalidates the sidecar
     with open(a, "a") as fh:
         fh.write("\n")
