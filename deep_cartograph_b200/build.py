@@ -45,18 +45,40 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+OBJ_DIR = os.path.join(PKG_DIR, "build")
+
+
+def _compile_one(src: str, verbose: bool):
+    obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
+    cmd = [_nvcc()] + [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else []) + \
+          ["-I", INCLUDE, "-c", src, "-o", obj]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    return obj, cmd, res
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every CUDA source for sm_100a into one shared library; returns its path."""
+    """Compile every CUDA source for sm_100a (one nvcc process per file, in parallel) and link
+    them into one shared library; returns its path."""
     if not force and not _stale():
         return LIB_PATH
+    from concurrent.futures import ThreadPoolExecutor
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-I", INCLUDE, "-o", LIB_PATH + ".tmp"] + sources() + ["-lcuda"]
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    srcs = sources()
+    with ThreadPoolExecutor(max_workers=min(len(srcs), os.cpu_count() or 1)) as pool:
+        results = list(pool.map(lambda s: _compile_one(s, verbose), srcs))
+    objs = []
+    for obj, cmd, res in results:
+        if verbose:
+            sys.stderr.write(res.stderr)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+        objs.append(obj)
+    cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC",
+           "-o", LIB_PATH + ".tmp"] + objs + ["-lcuda"]
     res = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose:
-        sys.stderr.write(res.stderr)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+        raise RuntimeError("nvcc link failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
     os.replace(LIB_PATH + ".tmp", LIB_PATH)
     return LIB_PATH
 
