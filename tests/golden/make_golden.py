@@ -67,6 +67,14 @@ def main():
         out[f"{cv}_cluster_cv"] = cl.iloc[:, :2].to_numpy(dtype=np.float64)
         out[f"{cv}_cluster_label"] = cl["cluster"].to_numpy(dtype=np.int64)
         out[f"{cv}_cluster_centroid"] = cl["centroid"].to_numpy(dtype=bool)
+    # DeepTICA: the reference's golden TorchScript model and the projection CSV it pins
+    # (tests/test_traj_projection.py); the model file is copied as a fixture, it loads with plain torch
+    import shutil
+    shutil.copy(os.path.join(DATA, "input", "models", "deep_tica_model.zip"),
+                os.path.join(HERE, "deep_tica_model.zip"))
+    csv = pd.read_csv(os.path.join(DATA, "reference", "train_colvars", "deep_tica_projected_trajectory.csv"))
+    out["deep_tica_csv"] = csv.to_numpy(dtype=np.float64)
+    out["deep_tica_csv_cols"] = np.array(list(csv.columns))
     np.savez_compressed(os.path.join(HERE, "peptide_c1.npz"), **out)
 
     # colvars text form for the step-API tests (float32 round-trips with 9 significant digits)

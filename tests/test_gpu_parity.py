@@ -896,6 +896,16 @@ def test_train_colvars_step_api_reproduces_golden(dev, c1, tmp_path, engine):
         np.testing.assert_allclose(calc.features_norm_range, c1[f"{cv}_features_norm_range"], rtol=1e-6)
 
 
+def test_golden_deeptica_model_through_the_calculator(dev, c1, tmp_path):
+    """The reference's tests/test_traj_projection.py for deep_tica: `CVCalculator.load` on the golden
+    model.zip and `project_data` on the device reproduce the golden CSV."""
+    from deep_cartograph_b200.modules.cv_learning import CVCalculator
+    calc = CVCalculator.load(os.path.join(GOLDEN, "deep_tica_model.zip"), str(tmp_path / "deeptica_load"))
+    assert calc.get_cv_dimension() == 2 and calc.get_cv_type() == "non-linear"
+    P = calc.project_data(torch.from_numpy(c1["X"].copy())).cpu().numpy()
+    np.testing.assert_allclose(P, c1["deep_tica_csv"], atol=6e-5)
+
+
 def test_train_colvars_from_binary_sidecar_equals_text_path(dev, tmp_path):
     """with a fresh float32 sidecar next to the colvars file the step reads the
     memory-mapped table (no text parsing) and produces the same models and projections, including

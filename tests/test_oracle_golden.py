@@ -5,10 +5,14 @@ Fixtures come from ``tests/golden/make_golden.py`` (reference test data:
 ``tests/data/reference/traj_cluster/*.csv``) and from the reference's own
 ``statistics.cluster_data`` for KMeans.
 """
+import json
+import os
+
 import numpy as np
 import pytest
 
 import oracle
+from conftest import GOLDEN
 
 
 def _standardized(c1, cv):
@@ -178,3 +182,22 @@ def test_deeptica_loss_matches_torch_autograd_free_form():
     ev = torch.linalg.eigvalsh(Li @ Ct @ Li.T).flip(0)
     np.testing.assert_allclose(evals, ev.numpy(), rtol=1e-10)
     assert np.isclose(loss, -(ev ** 2).sum().item())
+
+
+def test_reference_deeptica_model_reproduces_its_golden_projection(c1):
+    """the reference's golden DeepTICA model (TorchScript `cv_weights.pt` inside
+    `deep_tica_model.zip`, loadable with plain torch) maps the C1 features onto the golden
+    `deep_tica_projected_trajectory.csv` to print precision -- the fixture that pins A12."""
+    import io
+    import zipfile
+    import torch
+    z = zipfile.ZipFile(os.path.join(GOLDEN, "deep_tica_model.zip"))
+    meta = json.loads(z.read("model/metadata.json"))
+    assert meta == {"cv_name": "deep_tica", "cv_dimension": 2}
+    labels = z.read("model/features_labels.txt").decode().strip().split("\n")
+    assert labels == [str(v) for v in c1["features"]]
+    model = torch.jit.load(io.BytesIO(z.read("model/cv_weights.pt")), map_location="cpu")
+    with torch.no_grad():
+        P = model(torch.from_numpy(c1["X"].copy())).numpy()
+    assert list(c1["deep_tica_csv_cols"]) == ["DeepTIC 1", "DeepTIC 2"]
+    np.testing.assert_allclose(P, c1["deep_tica_csv"], atol=5.1e-5)
