@@ -622,6 +622,21 @@ def test_kmeans_empty_cluster_relocation(dev):
     np.testing.assert_allclose(centers, res["centers"], rtol=1e-12, atol=1e-13)
 
 
+def test_cluster_scores_on_device_match_sklearn(dev):
+    """K2 (reference statistics.py:73-74): Calinski-Harabasz and Davies-Bouldin computed on the device
+    from per-cluster FP64 sums equal scikit-learn's."""
+    from sklearn.metrics import calinski_harabasz_score, davies_bouldin_score
+    from deep_cartograph_b200.modules.statistics import statistics
+    rng = np.random.default_rng(4)
+    k, d, n = 7, 3, 20000
+    cent = rng.uniform(-1, 1, size=(k, d))
+    X = cent[rng.integers(0, k, size=n)] + 0.1 * rng.standard_normal((n, d))
+    labels, centers = statistics.cluster_data(X, {"algorithm": "kmeans", "num_clusters": k, "n_init": 1}, X[:k].copy())
+    sc = statistics.cluster_scores(X, labels)
+    assert abs(sc["calinski_harabasz"] - calinski_harabasz_score(X, labels)) <= 1e-9 * sc["calinski_harabasz"]
+    assert abs(sc["davies_bouldin"] - davies_bouldin_score(X, labels)) <= 1e-9
+
+
 def test_kmeans_full_size_c5_properties(dev):
     """BASELINE config C5, one GPU's share (12.5M frames x 10, k = 1000, float32) through
     size-independent properties of a Lloyd E-step: every frame is counted once, the per-cluster sums
