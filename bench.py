@@ -86,9 +86,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Summary of the samples that arrived inside [t_begin, t_end] (host clock; the sampler is
+        started before the warm-up so that nvidia-smi is already looping when the timed region
+        begins -- its start-up alone is longer than a short timed region)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -98,7 +101,8 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = [r for t, r in self.rows if (t_begin is None or t >= t_begin) and (t_end is None or t <= t_end + 0.02)]
+        for r in rows:
             parts = [p.strip() for p in r.split(",")]
             if len(parts) < 6:
                 continue
@@ -343,20 +347,22 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                    # before the warm-up: nvidia-smi needs ~0.2 s to start looping
     for _ in range(max(args.warmup, 3)):
         step()
     sync_all()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     launches0 = ops.KERNEL_LAUNCHES
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    host_t0 = time.perf_counter()
     t0.record()
     for _ in range(args.steps):
         evals, labels = step(record=True)
     t1.record()
     sync_all()
-    clocks = sampler.stop() if rank == 0 else None
+    host_t1 = time.perf_counter()
+    clocks = sampler.stop(host_t0, host_t1) if rank == 0 else None
     launches = ops.KERNEL_LAUNCHES - launches0
     ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
     cov_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in cov_ev) / len(cov_ev)], dtype=torch.float64, device=dev)
