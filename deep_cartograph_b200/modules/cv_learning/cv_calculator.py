@@ -288,7 +288,7 @@ class CVCalculator:
                 events.append(e)
         parts, acc, norm0, start = [], None, None, 0
         engine = self.backend.get("cov_engine")
-        if plan is not None:
+        if plan is not None and self.feats_norm_mode is not None:
             # provisional parameters: statistics of ~2048 evenly spaced rows, taken on the host before
             # any byte has moved (spans the whole series, so slow drifts do not bias it the way the
             # first chunk's statistics would)
@@ -296,7 +296,7 @@ class CVCalculator:
             smp = X.index_select(0, idx).to(torch.float64)
             m = smp.shape[0]
             mu = smp.mean(dim=0)
-            norm0 = self._provisional_norm({
+            norm0 = None if self.feats_norm_mode is None else self._provisional_norm({
                 "n": m, "mean": mu.to(dev), "m2": ((smp - mu) ** 2).sum(dim=0).to(dev),
                 "min": smp.min(dim=0).values.to(torch.float32).to(dev),
                 "max": smp.max(dim=0).values.to(torch.float32).to(dev)})
@@ -308,8 +308,8 @@ class CVCalculator:
             lag, block, want_st = plan
             if c1 - start <= lag:
                 continue
-            s = ops.lagged_covariance(data[start:c1], lag, norm0[0], norm0[1], block=block,
-                                      engine=engine, want_st=want_st)
+            s = ops.lagged_covariance(data[start:c1], lag, norm0[0] if norm0 else None,
+                                      norm0[1] if norm0 else None, block=block, engine=engine, want_st=want_st)
             if acc is None:
                 acc = s
             else:
@@ -516,11 +516,20 @@ class LinearCalculator(CVCalculator):
         return P
 
     # ---- shared by TICA / hTICA / PCA ---------------------------------------------------------
+    def _kernel_norm(self):
+        """(mean, range) handed to the fused kernels, or (None, None) when ``features_normalization``
+        is None: raw features are then contracted as they are, and the ``auto`` engine stays on
+        3xTF32 (FP16 pieces overflow at |x| >= 65504 and lose their low piece to subnormals for tiny
+        features)."""
+        if self.feats_norm_mode is None:
+            return None, None
+        return self._norm_on_device()
+
     def _lagged_sums(self, lag: int, block: int = 0, want_st: bool = True) -> dict:
         """Raw FP64 sums over the time-lagged pairs of this rank's shard (+ halo), summed over
         ranks.  Pairs: x_t = Z[:N-lag], x_lag = Z[lag:] on the CONCATENATED series (files are
         one time series, reference :278-300, 2247)."""
-        mean, rng = self._norm_on_device()
+        mean, rng = self._kernel_norm()
         X = self.training_data
         if self.shards is not None:
             X = self.shards.with_halo(X, lag)
@@ -530,9 +539,11 @@ class LinearCalculator(CVCalculator):
             s = ops.lagged_covariance(X, lag, mean, rng, block=block, engine=engine, want_st=want_st)
         if self.shards is not None:
             s = self.shards.allreduce_sums(s, m_total=(self.num_frames - lag) if self.num_frames else None)
-        if not s.get("_S0_full"):
-            s["S0"] = ops.symmetrize_upper(s["S0"])
-        s.pop("_S0_full", None)
+        # ALWAYS rebuild the lower triangle from the upper one after the reduction: a rank that kept
+        # its speculative sums contributes a full symmetric S0, a rank that recomputed contributes the
+        # upper triangle only (the kernel skips tiles below the diagonal) -- the upper triangle of the
+        # sum is right in both cases, the lower one only if every rank made the same choice.
+        s["S0"] = ops.symmetrize_upper(s["S0"])
         return s
 
     def _take_speculative_sums(self, X, lag, block, want_st, mean, rng, engine):
@@ -544,13 +555,19 @@ class LinearCalculator(CVCalculator):
         spec, self._spec = getattr(self, "_spec", None), None
         if spec is None or spec["plan"] != (lag, block, want_st):
             return None
-        m0, r0 = spec["norm0"]
-        be = ((m0.double() - mean.double()) / rng.double()).abs().max()
-        al = r0.double() / rng.double()
-        worst = torch.stack([be, al.max(), 1.0 / al.min()]).tolist()
-        if not (worst[0] <= 1.0 and worst[1] <= 2.0 and worst[2] <= 2.0):
-            logger.debug("Speculative sums discarded (provisional statistics off by %.2f sigma)" % worst[0])
+        norm0 = spec["norm0"]
+        if (norm0 is None) != (mean is None):
             return None
+        if norm0 is not None:
+            m0, r0 = norm0
+            be = ((m0.double() - mean.double()) / rng.double()).abs().max()
+            al = r0.double() / rng.double()
+            worst = torch.stack([be, al.max(), 1.0 / al.min()]).tolist()
+            if not (worst[0] <= 1.0 and worst[1] <= 2.0 and worst[2] <= 2.0):
+                logger.debug("Speculative sums discarded (provisional statistics off by %.2f sigma)" % worst[0])
+                return None
+        else:
+            m0 = r0 = None
         s = spec["sums"]
         done = spec["rows_done"]                               # pairs t < done - lag are in `s`
         if X.shape[0] > done:                                  # lag halo of the next shard arrived since
@@ -559,13 +576,12 @@ class LinearCalculator(CVCalculator):
                 if t.get(k) is not None:
                     s[k] += t[k]
             s["M"] += t["M"]
+        if norm0 is None:
+            return s                                           # raw features: the sums are already exact
+        # restandardize_sums needs the full symmetric S0 (outside the diagonal blocks of a block-mode
+        # pass the kernel leaves zeros and the consumers never look)
         s["S0"] = ops.symmetrize_upper(s["S0"])
-        if block:
-            # outside the diagonal blocks the kernel leaves zeros and the consumers never look
-            pass
-        out = linalg.restandardize_sums(s, m0, r0, mean, rng)
-        out["_S0_full"] = True
-        return out
+        return linalg.restandardize_sums(s, m0, r0, mean, rng)
 
 
 class PCACalculator(LinearCalculator):

@@ -176,9 +176,11 @@ def create_matrix_from_sidecars(colvars_paths: Union[List[str], str],
         for r0 in range(0, len(rows), chunk_rows):
             rr = rows[r0:r0 + chunk_rows]
             block = mm[rr[0]:rr[-1] + 1:stride] if stride >= 1 else mm[rr]
-            block = block[:, idx[0]:idx[-1] + 1] if contiguous_cols else block[:, idx]
+            # like the text path: a NaN in ANY column of the selected rows is an error, also in
+            # columns that are dropped or not selected afterwards
             if np.isnan(block).any():
                 raise ValueError(f"Clean your data! NaNs found in {path}")
+            block = block[:, idx[0]:idx[-1] + 1] if contiguous_cols else block[:, idx]
             out[o:o + len(rr)] = block
             o += len(rr)
         labels[o - len(rows):o] = file_idx

@@ -24,8 +24,20 @@ def _count(n: int) -> None:
     KERNEL_LAUNCHES += n
 
 
-def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def _stream(dev) -> int:
+    """torch's current stream ON THE DEVICE OF THE TENSORS (not of the current device)."""
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _call(dev, fn: str, *args) -> None:
+    """Library call in the device context of the tensors: ``backend.device`` may name a GPU that is
+    not torch's current one, and the library keys its attribute caches / arch checks / launches on
+    ``cudaGetDevice``."""
+    if dev.index is not None and dev.index != torch.cuda.current_device():
+        with torch.cuda.device(dev):
+            _lib.call(fn, *args)
+    else:
+        _lib.call(fn, *args)
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -89,8 +101,8 @@ def column_stats(X: torch.Tensor) -> dict:
     max_rows = 65535 * 1024
     if n <= max_rows:
         ws = _ws(lib.dcg_colstats_workspace_bytes(n, f), dev)
-        _lib.call("dcg_colstats_f32", X.data_ptr(), n, f, ld, mean.data_ptr(), m2.data_ptr(),
-                  mn.data_ptr(), mx.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+        _call(X.device, "dcg_colstats_f32", X.data_ptr(), n, f, ld, mean.data_ptr(), m2.data_ptr(),
+                  mn.data_ptr(), mx.data_ptr(), ws.data_ptr(), ws.numel(), _stream(X.device))
         _count(2)
         return {"n": n, "mean": mean, "m2": m2, "min": mn, "max": mx}
     parts = [column_stats(X[s:s + max_rows]) for s in range(0, n, max_rows)]
@@ -129,8 +141,8 @@ def standardize_(X: torch.Tensor, mean: torch.Tensor, rng: torch.Tensor) -> torc
         raise ValueError("mean / range length must equal the number of columns")
     if n == 0:
         return X
-    _lib.call("dcg_standardize_f32", X.data_ptr(), n, f, ld, mean.contiguous().data_ptr(),
-              rng.contiguous().data_ptr(), _stream())
+    _call(X.device, "dcg_standardize_f32", X.data_ptr(), n, f, ld, mean.contiguous().data_ptr(),
+              rng.contiguous().data_ptr(), _stream(X.device))
     _count(1)
     return X
 
@@ -163,9 +175,9 @@ def lagged_covariance(X: torch.Tensor, lag: int, mean: Optional[torch.Tensor] = 
     a = torch.empty(f, dtype=torch.float64, device=dev)
     b = torch.empty(f, dtype=torch.float64, device=dev)
     ws = _ws(lib.dcg_cov_workspace_bytes(n, f, lag, block, eng), dev)
-    _lib.call("dcg_cov_lag_f32", X.data_ptr(), n, f, ld, lag, _ptr(mean), _ptr(rng), block,
+    _call(X.device, "dcg_cov_lag_f32", X.data_ptr(), n, f, ld, lag, _ptr(mean), _ptr(rng), block,
               _ptr(S0), _ptr(St), a.data_ptr(), b.data_ptr(), eng, ws.data_ptr(), ws.numel(),
-              _stream())
+              _stream(X.device))
     _count(2 if eng == _lib.COV_SIMT_F32 else 3)      # colsum + engine (+ split reduction)
     return {"S0": S0, "St": St, "a": a, "b": b, "M": n - lag}
 
@@ -206,8 +218,8 @@ def project(X: torch.Tensor, W: torch.Tensor, mean: Optional[torch.Tensor] = Non
     if n == 0:
         return P, pmin, pmax
     ws = _ws(lib.dcg_project_workspace_bytes(n, f, d), dev)
-    _lib.call("dcg_project_f32", X.data_ptr(), n, f, ld, _ptr(mean), _ptr(rng), W.data_ptr(), d,
-              P.data_ptr(), _ptr(pmin), _ptr(pmax), ws.data_ptr(), ws.numel(), _stream())
+    _call(X.device, "dcg_project_f32", X.data_ptr(), n, f, ld, _ptr(mean), _ptr(rng), W.data_ptr(), d,
+              P.data_ptr(), _ptr(pmin), _ptr(pmax), ws.data_ptr(), ws.numel(), _stream(X.device))
     passes, nr = (d + 15) // 16, -(-f // 1024)
     if nr > 1 and X.data_ptr() % 16 == 0 and ld % 4 == 0:     # several feature ranges: row batches + combine
         cap = max(16, ((256 << 20) // (nr * 64)) // 16 * 16)
@@ -245,8 +257,8 @@ def project_blocks(X: torch.Tensor, W: torch.Tensor, block: int, mean: Optional[
     if n == 0:
         return P
     ws = _ws(lib.dcg_project_blocks_workspace_bytes(n, f, block), dev)
-    _lib.call("dcg_project_blocks_f32", X.data_ptr(), n, f, ld, _ptr(mean), _ptr(rng), W.data_ptr(), block, s,
-              P.data_ptr(), cols, ws.data_ptr(), ws.numel(), _stream())
+    _call(X.device, "dcg_project_blocks_f32", X.data_ptr(), n, f, ld, _ptr(mean), _ptr(rng), W.data_ptr(), block, s,
+              P.data_ptr(), cols, ws.data_ptr(), ws.numel(), _stream(X.device))
     _count(2)
     return P
 
@@ -292,9 +304,9 @@ def kmeans_step(Y: torch.Tensor, centers: torch.Tensor, labels: torch.Tensor,
     stats = torch.empty(3, dtype=torch.float64, device=dev)
     gap = torch.empty(n, dtype=Y.dtype, device=dev) if want_gap else None
     ws = _ws(256, dev)
-    _lib.call("dcg_kmeans_step", Y.data_ptr(), n, d, ld, _dtype_bytes(Y), centers.data_ptr(), k,
+    _call(Y.device, "dcg_kmeans_step", Y.data_ptr(), n, d, ld, _dtype_bytes(Y), centers.data_ptr(), k,
               labels.data_ptr(), _ptr(sums), _ptr(counts), stats.data_ptr(), _ptr(gap),
-              1 if update_sums else 0, _absmax_ptr(absmax, dev), ws.data_ptr(), ws.numel(), _stream())
+              1 if update_sums else 0, _absmax_ptr(absmax, dev), ws.data_ptr(), ws.numel(), _stream(Y.device))
     _count(1)
     return {"sums": sums, "counts": counts, "stats": stats, "gap": gap}
 
@@ -320,9 +332,9 @@ def kmeans_step_packed_(Y: torch.Tensor, centers: torch.Tensor, labels: torch.Te
         ws = _KM_WS[Y.device] = _ws(256, Y.device)
     o = k * d
     base = work.data_ptr()
-    _lib.call("dcg_kmeans_step", Y.data_ptr(), n, d, ld, _dtype_bytes(Y), centers.data_ptr(), k,
+    _call(Y.device, "dcg_kmeans_step", Y.data_ptr(), n, d, ld, _dtype_bytes(Y), centers.data_ptr(), k,
               labels.data_ptr(), base, base + 8 * o, base + 8 * (o + k), None, 1,
-              _absmax_ptr(absmax, Y.device), ws.data_ptr(), ws.numel(), _stream())
+              _absmax_ptr(absmax, Y.device), ws.data_ptr(), ws.numel(), _stream(Y.device))
     _count(1)
     return {"sums": work[:o].view(k, d), "counts": work[o:o + k], "stats": work[o + k:o + k + 3],
             "packed": work[:o + k + 3]}
@@ -341,8 +353,8 @@ def kmeans_update_(centers: torch.Tensor, sums: torch.Tensor, counts: torch.Tens
     k, d = centers.shape
     if info is None:
         info = torch.empty(2, dtype=torch.float64, device=centers.device)
-    _lib.call("dcg_kmeans_update", sums.data_ptr(), counts.data_ptr(), k, d, centers.data_ptr(),
-              info.data_ptr(), _stream())
+    _call(sums.device, "dcg_kmeans_update", sums.data_ptr(), counts.data_ptr(), k, d, centers.data_ptr(),
+              info.data_ptr(), _stream(sums.device))
     _count(1)
     return info
 
@@ -368,9 +380,9 @@ def kmeans_iterate_(Y: torch.Tensor, centers: torch.Tensor, labels: torch.Tensor
     ws = _KM_WS.get(Y.device)
     if ws is None:
         ws = _KM_WS[Y.device] = _ws(256, Y.device)
-    _lib.call("dcg_kmeans_iterate", Y.data_ptr(), n, d, ld, _dtype_bytes(Y), centers.data_ptr(), k,
+    _call(Y.device, "dcg_kmeans_iterate", Y.data_ptr(), n, d, ld, _dtype_bytes(Y), centers.data_ptr(), k,
               labels.data_ptr(), work.data_ptr(), _absmax_ptr(absmax, Y.device), ws.data_ptr(), ws.numel(),
-              _stream())
+              _stream(Y.device))
     _count(2)
     o = k * d
     return {"sums": work[:o].view(k, d), "counts": work[o:o + k], "stats": work[o + k:o + k + 3],
@@ -388,8 +400,8 @@ def nearest_to_centers(Y: torch.Tensor, centers: torch.Tensor) -> torch.Tensor:
     centers = centers.contiguous()
     out = torch.empty(k, dtype=torch.int64, device=dev)
     ws = _ws(lib.dcg_nearest_workspace_bytes(n, d, k), dev)
-    _lib.call("dcg_nearest_to_centers", Y.data_ptr(), n, d, ld, _dtype_bytes(Y), centers.data_ptr(),
-              k, out.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+    _call(Y.device, "dcg_nearest_to_centers", Y.data_ptr(), n, d, ld, _dtype_bytes(Y), centers.data_ptr(),
+              k, out.data_ptr(), ws.data_ptr(), ws.numel(), _stream(Y.device))
     _count(2)
     return out
 
@@ -412,8 +424,8 @@ def ticacov_sums(f: torch.Tensor, g: torch.Tensor, w: Optional[torch.Tensor] = N
         w = w.to(torch.float32).contiguous()
     if wl is not None:
         wl = wl.to(torch.float32).contiguous()
-    _lib.call("dcg_ticacov_f32", f.data_ptr(), g.data_ptr(), _ptr(w), _ptr(wl), B, d,
-              out.data_ptr(), _stream())
+    _call(f.device, "dcg_ticacov_f32", f.data_ptr(), g.data_ptr(), _ptr(w), _ptr(wl), B, d,
+              out.data_ptr(), _stream(f.device))
     _count(1)
     o = 2 + d
     return {"flat": out, "sw": out[0], "swl": out[1], "swf": out[2:o],
@@ -430,7 +442,7 @@ def ticaloss(sums: torch.Tensor, d: int, reg: float, n_eig: int = 0) -> dict:
     if n_out == 0 or sums.numel() < lib.dcg_ticacov_out_doubles(d) or not sums.is_contiguous():
         raise ValueError("sums must be the contiguous output of ticacov_sums with 1 <= d <= 32")
     res = torch.empty(n_out, dtype=torch.float64, device=sums.device)
-    _lib.call("dcg_ticaloss_f64", sums.data_ptr(), d, float(reg), int(n_eig), res.data_ptr(), _stream())
+    _call(sums.device, "dcg_ticaloss_f64", sums.data_ptr(), d, float(reg), int(n_eig), res.data_ptr(), _stream(sums.device))
     _count(1)
     o = 4
     return {"loss": res[0], "status": res[1], "sw": res[2], "swl": res[3], "evals": res[o:o + d],
@@ -452,8 +464,8 @@ def gather_standardize(X: torch.Tensor, idx: torch.Tensor, mean: torch.Tensor, r
     Z = torch.empty((nb, f), dtype=torch.float32, device=X.device)
     if nb == 0:
         return Z
-    _lib.call("dcg_gather_standardize_f32", X.data_ptr(), n, f, ld, idx.data_ptr(), nb, int(offset),
-              mean.contiguous().data_ptr(), rng.contiguous().data_ptr(), Z.data_ptr(), _stream())
+    _call(X.device, "dcg_gather_standardize_f32", X.data_ptr(), n, f, ld, idx.data_ptr(), nb, int(offset),
+              mean.contiguous().data_ptr(), rng.contiguous().data_ptr(), Z.data_ptr(), _stream(X.device))
     _count(1)
     return Z
 
@@ -472,7 +484,7 @@ def gen_eig_small(H: torch.Tensor, G: torch.Tensor):
     theta = torch.empty((nb, b), dtype=torch.float64, device=H.device)
     S = torch.empty((nb, b, b), dtype=torch.float64, device=H.device)
     status = torch.empty(nb, dtype=torch.float64, device=H.device)
-    _lib.call("dcg_gen_eig_small_f64", H.data_ptr(), G.data_ptr(), b, nb, theta.data_ptr(), S.data_ptr(),
-              status.data_ptr(), _stream())
+    _call(H.device, "dcg_gen_eig_small_f64", H.data_ptr(), G.data_ptr(), b, nb, theta.data_ptr(), S.data_ptr(),
+              status.data_ptr(), _stream(H.device))
     _count(1)
     return theta, S, status
