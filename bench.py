@@ -51,6 +51,9 @@ def parse_args():
     ap.add_argument("--features", type=int, default=F)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-legs", action="store_true", help="skip the C3 (hTICA 4950 features) and C5 (KMeans k=1000) legs")
+    ap.add_argument("--no-parity", action="store_true", help="skip the float64 parity block")
+    ap.add_argument("--c3-frames", type=int, default=0, help="total frames of the C3 leg (default 10M, 1.25M at 1 GPU)")
     return ap.parse_args()
 
 
@@ -241,6 +244,166 @@ def emit_json(line) -> None:
     else:
         sys.stdout.flush()
         os.write(_JSON_FD, data)
+
+
+# ----------------------------------------------------------------------------------------------
+# parity block and the sharded north_star legs (C3, C5)
+# ----------------------------------------------------------------------------------------------
+def parity_block(X, lag, d, engine):
+    """float64 check of THIS run's kernels on this rank's resident shard (all rows): full S0 / S_tau,
+    eigenvalues, eigenvectors (max column L2 distance up to sign) and normalised projections against
+    oracle/float64_device.py.  The oracle is the checker here, never the thing timed."""
+    import torch
+    from deep_cartograph_b200 import linalg, ops
+    from oracle import float64_device as f64
+    n = X.shape[0]
+    st = ops.column_stats(X)
+    mean = st["mean"].float()
+    rng = torch.sqrt(st["m2"] / (n - 1)).float()
+    s = ops.lagged_covariance(X, lag, mean, rng, engine=engine)
+    ref = f64.lagged_sums(X, lag, mean, rng)
+    err = f64.sums_rel_error(s, ref)
+    ev, V = linalg.tica_from_sums(ops.symmetrize_upper(s["S0"]), s["St"], s["a"], s["b"], s["M"], d)
+    ev_ref, V_ref = f64.tica_from_sums(ref["S0"], ref["St"], ref["a"], ref["b"], ref["M"], d)
+    P, pmin, pmax = ops.project(X, V.float(), mean, rng)
+    ops.standardize_(P, (pmax + pmin) / 2, (pmax - pmin) / 2)
+    Pn_ref, _, _ = f64.project_normalized(X, mean, rng, V_ref)
+    sgn = torch.sign((V * V_ref).sum(0, keepdim=True))
+    out = {"frames": n, "engine": engine, "cov_rel_err": max(err["S0"], err["St"]),
+           "eval_rel_err": float(((ev - ev_ref).abs() / ev_ref.abs()).max()),
+           "evec_err": f64.eigvec_error(V, V_ref),
+           "proj_err": float((P.double() * sgn - Pn_ref).abs().max()),
+           "tolerances": {"cov": 1e-5, "eval": 1e-5, "evec": 1e-5, "proj": 1e-4},
+           "checker": "oracle/float64_device.py (torch float64 on the device, dense Cholesky route)"}
+    out["ok"] = bool(out["cov_rel_err"] <= 1e-5 and out["eval_rel_err"] <= 1e-5 and out["evec_err"] <= 1e-5
+                     and out["proj_err"] <= 1e-4)
+    return out
+
+
+def _max_over_ranks(ms, dev, shards):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(ms, dtype=torch.float64, device=dev)
+    if shards is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.tolist()
+
+
+def run_c3_leg(args, dev, rank, world, shards, peaks):
+    """north_star target configuration C3: 10M frames x 4950 features, hTICA (10 subspaces of 495 ->
+    5 each -> d = 10, lag 10) + projection + KMeans(k = 1000, 5 Lloyd iterations), frames sharded over
+    the GPUs (strong scaling: the TOTAL is fixed).  At 1 GPU the matrix (198 GB) does not fit: the leg
+    then runs one GPU's share of the 8-GPU run (1.25M frames, 24.75 GB) and says so."""
+    import torch
+    from deep_cartograph_b200 import linalg, ops
+    from deep_cartograph_b200.modules.cv_learning.cv_calculator import HTICACalculator
+    from deep_cartograph_b200.modules.statistics import statistics
+    from deep_cartograph_b200.synthetic import feature_matrix
+    f, lag, d, k, iters = 4950, LAG, 10, 1000, 5
+    total = args.c3_frames or (10_000_000 if world > 1 else 1_250_000)
+    s0, s1 = (rank * total) // world, ((rank + 1) * total) // world
+    n = s1 - s0
+    ld = (f + 3) // 4 * 4
+    buf = torch.empty((n + lag, ld), dtype=torch.float32, device=dev)
+    for c0 in range(0, n, 1 << 16):                          # bounded temporaries
+        c1 = min(n, c0 + (1 << 16))
+        feature_matrix(total, f, s0 + c0, s0 + c1, dev, n_slow=14, out=buf[c0:c1, :f])
+    X = buf[:n, :f]
+    cfg = {"dimension": d, "lag_time": lag, "features_normalization": "mean_std", "num_subspaces": 10,
+           "subspaces_dimension": 5, "backend": {"cov_engine": args.engine}}
+    outdir = os.path.join(ROOT, "gpurun_out", f"bench_c3_rank{rank}")
+    os.makedirs(outdir, exist_ok=True)
+
+    def ev():
+        e = torch.cuda.Event(enable_timing=True); e.record(); return e
+
+    def one():
+        t = [ev()]
+        calc = HTICACalculator(configuration=cfg, output_path=outdir)
+        calc.load_training_tensor(X, shards=shards)                  # statistics (+ all-gather merge)
+        t.append(ev())
+        calc.create_output_folders()
+        calc.compute_cv()                                            # level-1 block sums + eigen, block projection, level 2
+        t.append(ev())
+        calc.set_labels()
+        Pn = calc.normalize_cv()                                     # projection + CV min/max (+ all-reduce)
+        t.append(ev())
+        init = Pn[:k].to(torch.float64).clone()
+        if shards is not None:
+            shards.broadcast_(init, 0)
+        res = statistics.kmeans_lloyd(Pn, init, max_iter=iters, tol=0.0, shards=shards)
+        t.append(ev())
+        torch.cuda.synchronize()
+        assert calc.cv is not None and res["n_iter"] == iters
+        return [t[i].elapsed_time(t[i + 1]) for i in range(len(t) - 1)], calc
+
+    one()                                                            # warm-up
+    if shards is not None:
+        torch.distributed.barrier()
+    runs = []
+    for _ in range(2):
+        ms, calc = one()
+        runs.append(_max_over_ranks(ms, dev, shards))
+    ms = [min(r[i] for r in runs) for i in range(4)]
+    tot = sum(ms)
+    W = torch.as_tensor(calc.cv)
+    hbm = peaks["hbm_gbs"]
+    out = {"workload": f"C3: {total} frames x {f} features (row stride {ld}), hTICA 10 x 495 -> 50 -> {d}, lag {lag}, "
+                       f"projection, KMeans k={k} x {iters} Lloyd iterations; frames sharded x{world}",
+           "frames_total": total, "frames_per_gpu": n, "n_gpus": world, "scaling": "strong",
+           "ms": {"stats": ms[0], "htica_sums_eigen": ms[1], "projection": ms[2], "kmeans": ms[3], "total": tot},
+           "frames_per_s": total / (tot * 1e-3),
+           "frac_hbm": {"stats": 4.0 * ld * n / (ms[0] * 1e-3) / 1e9 / hbm,
+                        "projection": (4.0 * ld + 4.0 * d) * n / (ms[2] * 1e-3) / 1e9 / hbm},
+           "weights_finite": bool(torch.isfinite(W).all()), "eig_stats": dict(linalg.EIG_STATS)}
+    if world == 1 and total < 10_000_000:
+        out["note"] = ("one GPU cannot hold C3 (198 GB): this is ONE GPU's share of the 8-GPU run, resident; the "
+                       "8-GPU line's speed-up over it is (its frames_per_s) / (this frames_per_s)")
+    del buf, X
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_c5_leg(args, dev, rank, world, shards, peaks):
+    """C5: KMeans k = 1000 in a 10-D CV space, 12.5M float32 frames per GPU (100M at 8 GPUs, weak
+    scaling), fixed initial centroids = the first 1000 frames, 5 sharded Lloyd iterations through
+    statistics.kmeans_lloyd (one packed FP64 all-reduce per iteration)."""
+    import torch
+    from deep_cartograph_b200.modules.statistics import statistics
+    from deep_cartograph_b200.synthetic import cluster_points
+    n, d, k, iters = 12_500_000, 10, 1000, 5
+    Y = cluster_points(n, d, k, dev, seed=2, dtype=torch.float32, start=rank * n)
+    init = Y[:k].to(torch.float64).clone()
+    if shards is not None:
+        shards.broadcast_(init, 0)
+
+    def one():
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = statistics.kmeans_lloyd(Y, init, max_iter=iters, tol=0.0, shards=shards)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), res
+
+    one()
+    if shards is not None:
+        torch.distributed.barrier()
+    runs = [one() for _ in range(3)]
+    ms = min(_max_over_ranks([r[0]], dev, shards)[0] for r in runs)
+    res = runs[-1][1]
+    per_iter = ms / (iters + 1)                              # + the final E-step of the driver
+    fp32_peak = 148 * 128 * 2 * (peaks.get("sm_max_mhz") or 1965.0) * 1e6 / 1e12
+    out = {"workload": f"C5: KMeans k={k}, d={d}, {n} float32 frames per GPU x{world} (weak scaling), fixed init, "
+                       f"{iters} Lloyd iterations + final E-step, setup (centring, variance) included",
+           "frames_total": n * world, "n_gpus": world, "ms_total": ms, "ms_per_iteration": per_iter,
+           "frame_iterations_per_s": n * world * (iters + 1) / (ms * 1e-3),
+           "bound": "fp32 / tensor score GEMM + arg-min scan (k/2 = 500 FLOP/B, far above the HBM ridge)",
+           "tflops_useful": 2.0 * k * d * n * (iters + 1) / (ms * 1e-3) / 1e12, "fp32_peak_nominal": fp32_peak,
+           "ties": res["ties"], "n_iter": res["n_iter"]}
+    out["frac_fp32"] = out["tflops_useful"] / fp32_peak
+    del Y
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -478,6 +641,16 @@ def main():
         if numa_note:
             e2e["host_buffer"] = numa_note
 
+    parity = None
+    if rank == 0 and not args.no_parity:
+        parity = parity_block(X, LAG, DIM, engine)
+    c3 = c5 = None
+    if not args.no_legs:
+        del buf, X
+        torch.cuda.empty_cache()
+        c5 = run_c5_leg(args, dev, rank, world, shards, peaks)
+        c3 = run_c3_leg(args, dev, rank, world, shards, peaks)
+
     if rank == 0:
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
@@ -489,7 +662,8 @@ def main():
                           "tc_3xtf32": "f32 (tf32x3 split-precision tensor contraction, f64 accumulation)"}.get(engine, "f32"),
                 "data": "synthetic", "config": workload_config(args, world, engine),
                 "roofline": roofline, "passes": passes, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
-                "clocks": clocks, "eigenvalues": [float(v) for v in evals.cpu().tolist()]}
+                "clocks": clocks, "eigenvalues": [float(v) for v in evals.cpu().tolist()],
+                "parity": parity, "c3": c3, "c5": c5}
         emit_json(line)
     if shards is not None:
         dist.destroy_process_group()

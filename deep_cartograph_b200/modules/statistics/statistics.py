@@ -154,20 +154,45 @@ def kmeans_lloyd(Y: torch.Tensor, init_centers: torch.Tensor, max_iter: int = 30
 
 
 def _relocate_empty(Yc, C, labels, sums, counts, empty, shards):
-    """sklearn _relocate_empty_clusters_dense: move the farthest points into the empty clusters
-    (rare path, evaluated with torch ops on the device).  Labels are left untouched, as in sklearn."""
-    if shards is not None and shards.world > 1:
-        raise NotImplementedError("empty-cluster relocation across shards is not implemented")
+    """sklearn _relocate_empty_clusters_dense (sklearn/cluster/_k_means_common.pyx:167-211, reached from
+    reference statistics.py:189-195): the n_empty frames farthest from their centres become the new
+    centres of the empty clusters (in index order of the empty clusters), and leave their old ones.
+    Labels are left untouched, as in sklearn.  Rare path, torch ops on the device.
+
+    Frame-sharded: ``sums`` / ``counts`` are the already all-reduced (replicated) global ones; every
+    rank offers its n_empty farthest frames (distance, old label, coordinates), the candidates are
+    all-gathered, and every rank applies the same global top-n_empty -- ties go to the lower rank,
+    then the lower local index, i.e. the lower GLOBAL frame index of the contiguous shards."""
     n_empty = int(empty.numel())
+    n, d = Yc.shape
+    dev = Yc.device
     dist = ((Yc.to(torch.float64) - C[labels.long()]) ** 2).sum(dim=1)
-    far = torch.topk(dist, n_empty, largest=True, sorted=True).indices
+    m = min(n_empty, n)
+    top = torch.topk(dist, m, largest=True, sorted=True) if m > 0 else None
+    # candidates: [distance | old label | coordinates], best first; stable for equal distances
+    cand = torch.full((n_empty, 2 + d), float("-inf"), dtype=torch.float64, device=dev)
+    if m > 0:
+        far = top.indices
+        order = torch.argsort(far)                                  # equal distances: lower index first
+        far = far[order][torch.argsort(-dist[far[order]], stable=True)]
+        cand[:m, 0] = dist[far]
+        cand[:m, 1] = labels[far].to(torch.float64)
+        cand[:m, 2:] = Yc[far].to(torch.float64)
+    if shards is not None and shards.world > 1:
+        allc = torch.empty((shards.world * n_empty, 2 + d), dtype=torch.float64, device=dev)
+        torch.distributed.all_gather_into_tensor(allc, cand.contiguous(), group=shards.group)
+        # rank-major order + stable sort = ties to the lower global frame index
+        pick = torch.argsort(-allc[:, 0], stable=True)[:n_empty]
+        cand = allc[pick]
     sums = sums.clone()
     counts = counts.clone()
+    rows = cand.tolist()
     for idx in range(n_empty):
         new_id = int(empty[idx].item())
-        fi = int(far[idx].item())
-        old_id = int(labels[fi].item())
-        x = Yc[fi].to(torch.float64)
+        if rows[idx][0] == float("-inf"):
+            break                                                   # fewer frames than empty clusters
+        old_id = int(rows[idx][1])
+        x = cand[idx, 2:]
         sums[old_id] -= x
         sums[new_id] = x
         counts[new_id] = 1.0

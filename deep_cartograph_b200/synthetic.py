@@ -27,22 +27,38 @@ def latent_chains(n_total: int, n_slow: int, seed: int = 0, t0: float = 4000.0) 
     return z
 
 
+NOISE_CHUNK = 1 << 16       # rows per noise block; blocks sit on a GLOBAL grid (multiples of this)
+
+
 def feature_matrix(n_total: int, f: int, start: int, stop: int, device, seed: int = 0,
-                   n_slow: int = 8, noise: float = 0.5, chunk: int = 1 << 18) -> torch.Tensor:
-    """Rows [start, stop) of the synthetic (n_total x f) matrix, as a float32 tensor on ``device``."""
+                   n_slow: int = 8, noise: float = 0.5, out: torch.Tensor = None) -> torch.Tensor:
+    """Rows [start, stop) of the synthetic (n_total x f) matrix, as a float32 tensor on ``device``.
+
+    Every row is a pure function of (seed, f, global frame index): the feature noise is drawn in
+    blocks of NOISE_CHUNK rows on a global grid, block g from a generator seeded with (seed, g), and a
+    shard takes the rows of the blocks it overlaps -- so any sharding of the series (and any
+    ``start``) reproduces the same rows bit for bit on the same device type."""
     z = latent_chains(n_total, n_slow, seed)[start:stop]
     g = torch.Generator(device="cpu").manual_seed(seed + 1)
     A = torch.randn((n_slow, f), generator=g, dtype=torch.float32).to(device)
     s = (torch.rand(f, generator=g) * 0.45 + 0.05).to(device)
     m = (torch.rand(f, generator=g) * 2.5 + 0.5).to(device)
-    X = torch.empty((stop - start, f), dtype=torch.float32, device=device)
+    X = out if out is not None else torch.empty((stop - start, f), dtype=torch.float32, device=device)
     dg = torch.Generator(device=device)
-    for c0 in range(0, stop - start, chunk):
-        c1 = min(stop - start, c0 + chunk)
-        dg.manual_seed(seed * 1_000_003 + (start + c0))      # keyed by the global frame index
-        zc = torch.from_numpy(z[c0:c1]).to(device=device, dtype=torch.float32)
-        e = torch.randn((c1 - c0, f), generator=dg, dtype=torch.float32, device=device)
-        X[c0:c1] = (zc @ A + noise * e) * s + m
+    for blk in range(start // NOISE_CHUNK, (max(stop, start + 1) - 1) // NOISE_CHUNK + 1):
+        b0 = blk * NOISE_CHUNK
+        g0, g1 = max(start, b0), min(stop, b0 + NOISE_CHUNK)
+        if g1 <= g0:
+            continue
+        dg.manual_seed(seed * 1_000_003 + blk)                 # keyed by the global block index
+        e = torch.randn((NOISE_CHUNK, f), generator=dg, dtype=torch.float32, device=device)[g0 - b0:g1 - b0]
+        zc = torch.from_numpy(z[g0 - start:g1 - start]).to(device=device, dtype=torch.float32)
+        # zc @ A as n_slow elementwise rank-1 updates in a fixed order (not a GEMM, whose summation
+        # order depends on the shape heuristics): the rows must not depend on the shard shape
+        e *= noise
+        for k in range(n_slow):
+            e.addcmul_(zc[:, k:k + 1], A[k:k + 1])
+        X[g0 - start:g1 - start] = e * s + m
     return X
 
 

@@ -156,6 +156,19 @@ def _kmeans_worker(rank, world, port, out):
         assert res["n_iter"] == ref["n_iter"], (res["n_iter"], ref["n_iter"])
         np.testing.assert_array_equal(res["labels"].numpy(), ref["labels"][s:e])
         np.testing.assert_allclose(res["centers"].numpy(), ref["centers"], rtol=1e-12, atol=1e-12)
+        # ---- empty-cluster relocation across shards (sklearn _k_means_common.pyx:167-211): the third
+        # initial centre attracts nobody; the frame farthest from its centre lives on the LAST rank
+        # and must become the new centre on every rank
+        Y2 = np.concatenate([g.normal(0.0, 0.05, size=(40, 2)), g.normal(5.0, 0.05, size=(40, 2)),
+                             np.array([[9.0, 9.0]])])
+        init2 = np.array([[0.0, 0.0], [5.0, 5.0], [100.0, 100.0]])
+        s2, e2 = shard_range(len(Y2), rank, world)
+        res2 = statistics.kmeans_lloyd(torch.from_numpy(Y2[s2:e2]), torch.from_numpy(init2), shards=FrameShards())
+        ref2 = oracle.kmeans_lloyd(Y2, init2)
+        assert res2["n_iter"] == ref2["n_iter"]
+        np.testing.assert_array_equal(res2["labels"].numpy(), ref2["labels"][s2:e2])
+        np.testing.assert_allclose(res2["centers"].numpy(), ref2["centers"], rtol=1e-12, atol=1e-12)
+        assert np.bincount(ref2["labels"], minlength=3)[2] == 1          # the relocated centre kept its frame
         out.put((rank, "ok"))
     except Exception:  # noqa: BLE001
         import traceback

@@ -201,3 +201,34 @@ def test_reference_deeptica_model_reproduces_its_golden_projection(c1):
         P = model(torch.from_numpy(c1["X"].copy())).numpy()
     assert list(c1["deep_tica_csv_cols"]) == ["DeepTIC 1", "DeepTIC 2"]
     np.testing.assert_allclose(P, c1["deep_tica_csv"], atol=5.1e-5)
+
+
+def test_float64_device_checker_equals_numpy_oracle():
+    """oracle/float64_device.py (the torch float64 checker used at BASELINE sizes on the GPU box) is
+    the same function as the numpy oracle that is pinned to the reference's golden artefacts."""
+    import torch
+    from conftest import synth_features
+    from oracle import float64_device as f64
+    X = synth_features(3000, 37, seed=4)
+    st = oracle.column_stats(X)
+    m, r = oracle.prepare_normalization(st, "mean_std")
+    Z = oracle.standardize(X, m, r)
+    Xt, mt, rt = torch.from_numpy(X), torch.from_numpy(m.astype(np.float32)), torch.from_numpy(r.astype(np.float32))
+    lag = 7
+    s = f64.lagged_sums(Xt, lag, mt, rt, chunk=700)
+    ref = dict(zip(("S0", "St", "a", "b", "M"), oracle.lagged_sums(Z, lag)))
+    for k in ("S0", "St", "a", "b"):
+        np.testing.assert_allclose(s[k].numpy(), ref[k], rtol=1e-12, atol=1e-9)
+    assert s["M"] == ref["M"]
+    ev, V = f64.tica_from_sums(s["S0"], s["St"], s["a"], s["b"], s["M"], 3)
+    ev_o, V_o = oracle.tica(Z, lag, 3)
+    np.testing.assert_allclose(ev.numpy(), ev_o, rtol=1e-9)
+    np.testing.assert_allclose(V.numpy(), V_o, atol=1e-8)
+    W, T1, V2 = f64.htica(Xt, lag, mt, rt, 5, 3, 2, chunk=900)
+    W_o, _, _ = oracle.htica(Z, lag, 5, 3, 2)
+    np.testing.assert_allclose(W.numpy(), W_o, atol=1e-7)
+    Pn, mn, mx = f64.project_normalized(Xt, mt, rt, V, chunk=1000)
+    P = oracle.project(Z, V_o)
+    cm, cr = oracle.cv_normalization(P)
+    np.testing.assert_allclose(Pn.numpy(), (P - cm) / cr, atol=1e-7)
+    assert f64.eigvec_error(V, -torch.from_numpy(V_o)) < 1e-8
