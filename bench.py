@@ -30,6 +30,12 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# DRAM bytes (read + written) per launch of the dominant kernel, keyed by (engine, frames, features): from the
+# committed `ncu --set full` captures under profiles/ (dram__bytes_read.sum + dram__bytes_write.sum).  A shape
+# without a capture reports null.
+TRAFFIC = {("tc_3xf16", 1_000_000, 1000): 11.88e9, ("tc_3xtf32", 1_000_000, 1000): 9.95e9,
+           ("tc_i8x3", 1_000_000, 1000): 13.56e9}
+
 F = 1000
 N_PER_GPU = 1_000_000
 LAG = 10
@@ -45,8 +51,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--engine", default=os.environ.get("DCG_COV_ENGINE", "tc_3xf16"),
-                    choices=["tc_3xf16", "tc_3xtf32", "tc_1xtf32", "simt_f32"])
+    ap.add_argument("--engine", default=os.environ.get("DCG_COV_ENGINE", "tc_i8x3"),
+                    choices=["tc_i8x3", "tc_3xf16", "tc_3xtf32", "tc_1xtf32", "simt_f32"])
     ap.add_argument("--frames", type=int, default=N_PER_GPU, help="frames per GPU (default = C2)")
     ap.add_argument("--features", type=int, default=F)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -260,9 +266,11 @@ def parity_block(X, lag, d, engine):
     st = ops.column_stats(X)
     mean = st["mean"].float()
     rng = torch.sqrt(st["m2"] / (n - 1)).float()
-    s = ops.lagged_covariance(X, lag, mean, rng, engine=engine)
+    s = ops.lagged_covariance(X, lag, mean, rng, engine=engine, xmin=st["min"], xmax=st["max"])
     ref = f64.lagged_sums(X, lag, mean, rng)
     err = f64.sums_rel_error(s, ref)
+    if engine == "tc_i8x3":
+        err["St"] = err["St_sym"]          # the exact engine returns the symmetric part of St (all TICA uses)
     ev, V = linalg.tica_from_sums(ops.symmetrize_upper(s["S0"]), s["St"], s["a"], s["b"], s["M"], d)
     ev_ref, V_ref = f64.tica_from_sums(ref["S0"], ref["St"], ref["a"], ref["b"], ref["M"], d)
     P, pmin, pmax = ops.project(X, V.float(), mean, rng)
@@ -278,6 +286,15 @@ def parity_block(X, lag, d, engine):
     out["ok"] = bool(out["cov_rel_err"] <= 1e-5 and out["eval_rel_err"] <= 1e-5 and out["evec_err"] <= 1e-5
                      and out["proj_err"] <= 1e-4)
     return out
+
+
+def _log(msg):
+    if int(os.environ.get("RANK", "0")) == 0:
+        sys.stderr.write("[bench %7.1f s] %s\n" % (time.perf_counter() - _T0, msg))
+        sys.stderr.flush()
+
+
+_T0 = time.perf_counter()
 
 
 def _max_over_ranks(ms, dev, shards):
@@ -309,6 +326,8 @@ def run_c3_leg(args, dev, rank, world, shards, peaks):
         c1 = min(n, c0 + (1 << 16))
         feature_matrix(total, f, s0 + c0, s0 + c1, dev, n_slow=14, out=buf[c0:c1, :f])
     X = buf[:n, :f]
+    torch.cuda.synchronize()
+    _log(f"C3 leg: shard of {n} x {f} generated")
     cfg = {"dimension": d, "lag_time": lag, "features_normalization": "mean_std", "num_subspaces": 10,
            "subspaces_dimension": 5, "backend": {"cov_engine": args.engine}}
     outdir = os.path.join(ROOT, "gpurun_out", f"bench_c3_rank{rank}")
@@ -338,6 +357,7 @@ def run_c3_leg(args, dev, rank, world, shards, peaks):
         return [t[i].elapsed_time(t[i + 1]) for i in range(len(t) - 1)], calc
 
     one()                                                            # warm-up
+    _log("C3 leg: warm-up step done")
     if shards is not None:
         torch.distributed.barrier()
     runs = []
@@ -441,6 +461,7 @@ def main():
     X = buf[:n]
     torch.cuda.synchronize()
 
+    _log("C2 shard generated")
     cov_ev = []
     pass_ev = {k: [] for k in ("stats", "covariance", "eigen", "projection", "kmeans")}
 
@@ -474,7 +495,8 @@ def main():
         if record:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        s = ops.lagged_covariance(Xh, LAG, mean, rng, engine=engine)
+        s = ops.lagged_covariance(Xh, LAG, mean, rng, engine=engine, xmin=st["min"], xmax=st["max"])
+        s.pop("clamped", None)
         if record:
             e1.record()
             cov_ev.append((e0, e1))
@@ -517,6 +539,8 @@ def main():
         step()
     sync_all()
     launches0 = ops.KERNEL_LAUNCHES
+    if engine == "tc_i8x3":
+        ops.cov_i8_timing(True)            # CUDA events around the quantise and contraction kernels, on their stream
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     host_t0 = time.perf_counter()
     t0.record()
@@ -527,6 +551,10 @@ def main():
     host_t1 = time.perf_counter()
     clocks = sampler.stop(host_t0, host_t1) if rank == 0 else None
     launches = ops.KERNEL_LAUNCHES - launches0
+    i8t = None
+    if engine == "tc_i8x3":
+        i8t = ops.cov_i8_timing()
+        ops.cov_i8_timing(False)
     ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
     cov_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in cov_ev) / len(cov_ev)], dtype=torch.float64, device=dev)
     if shards is not None:
@@ -538,29 +566,52 @@ def main():
     # ---- roofline of the dominant kernel (covariance contraction)
     M = n - LAG if world == 1 else n            # pairs per rank (last rank has n - lag)
     alg_flops = 3.0 * f * f * M                  # 2F^2 (C_tau) + F^2 (upper C0) per pair
-    # peak of the chosen tensor-core precision: kind::f16 = the measured bf16 figure; dense TF32 is
-    # 1/2 of it on the tcgen05 pipe (K = 8 instead of 16 per instruction, same cycles)
-    # The kernel is timed inside a long step (20 back-to-back steps under the power cap), so the
-    # denominator is the SUSTAINED measured figure; the burst figure is reported beside it.
-    f16_kind = engine == "tc_3xf16"
-    tf32_peak = peaks["bf16_tflops_sustained"] if f16_kind else peaks["bf16_tflops_sustained"] / 2.0
-    burst_peak = peaks["bf16_tflops"] if f16_kind else peaks["bf16_tflops"] / 2.0
-    cov_s = float(cov_ms.item()) * 1e-3
-    achieved = alg_flops / cov_s / 1e12
-    issued_mult = {"tc_3xf16": 3.0, "tc_3xtf32": 3.0, "tc_1xtf32": 1.0, "simt_f32": 1.0}[engine]
-    # DRAM bytes per launch of this kernel at this shape, from the committed ncu --set full captures
-    # (dram__bytes_read.sum + dram__bytes_write.sum)
-    # (profiles/r1_cov_tc_f16x3_ncu_summary.txt / r1_cov_tc_v2_ncu_summary.txt)
-    traffic = {"tc_3xf16": 11.88e9, "tc_3xtf32": 9.95e9}.get(engine) if (n == N_PER_GPU and f == F) else None
-    roofline = {"bound": "tensor", "kernel": f"cov_lag ({engine})", "achieved": achieved, "peak": tf32_peak,
-                "unit": "TFLOP/s", "frac": achieved / tf32_peak, "traffic": traffic,
-                "traffic_note": "bytes/launch (ncu); algorithmic bytes/launch = 4*F*n = %.3g" % (4.0 * f * n),
-                "issued_tflops": achieved * issued_mult, "frac_issued": achieved * issued_mult / tf32_peak,
-                "kernel_ms": cov_s * 1e3, "share_of_step": cov_s * 1e3 / ms_per_step,
-                "peak_source": (f"{peaks['source']} bf16 sustained (kind::f16; kernel timed inside a long step)" if f16_kind else
-                                f"{peaks['source']} bf16 sustained / 2 (TF32 : bf16 = 1 : 2 on tcgen05)"),
-                "peak_burst": burst_peak, "frac_issued_of_burst": achieved * issued_mult / burst_peak,
-                "algorithmic": "3*F^2 FLOP per frame pair; issued = x3 for the split-precision engines"}
+    cov_s = float(cov_ms.item()) * 1e-3          # the whole dcg_cov_lag* call (all its kernels)
+    if engine == "tc_i8x3":
+        # dominant kernel = cov_i8_kernel (tcgen05 kind::i8), timed alone with CUDA events on its stream.
+        # peak: the MEASURED dense bf16 figure of MEASURED_PEAKS.json (the contract's tensor denominator;
+        # sustained: the kernel is timed inside a long step).  kind::i8 issues at twice the kind::f16 rate
+        # (measured: 64 clocks per 256 x 128 x 32 MMA pair-instruction), so the int8 peak derived from the
+        # same measurement is 2x; both fractions are reported.
+        k_ms = i8t["contract_ms"] / max(1, i8t["launches"])
+        q_ms = i8t["quantize_ms"] / max(1, i8t["launches"])
+        from deep_cartograph_b200 import _lib as _l
+        n_up = sum(1 for i0 in range(0, f, 256) for j0 in range(0, f, 128) if j0 + 128 > i0)
+        issued_ops = 2.0 * (2 * n_up) * 256 * 128 * 8 * M          # 2 Grams, 8 digit products, MAC = 2 ops
+        achieved = alg_flops / (k_ms * 1e-3) / 1e12
+        peak = peaks["bf16_tflops_sustained"]
+        roofline = {"bound": "tensor", "kernel": "cov_i8_kernel (tcgen05.mma.cta_group::2.kind::i8, TMA-staged digit planes)",
+                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                    "peak_source": f"{peaks['source']} dense bf16, sustained (MEASURED_PEAKS.json)",
+                    "kernel_ms": k_ms, "share_of_step": k_ms / ms_per_step,
+                    "algorithmic": "3*F^2 FLOP per frame pair (SURVEY 8d); the exact engine issues 8 int8 digit products "
+                                   "on 2 x %d upper-triangle tiles of 256 x 128" % n_up,
+                    "issued_int8_tops": issued_ops / (k_ms * 1e-3) / 1e12,
+                    "int8_peak_derived_tops": 2.0 * peaks["bf16_tflops"],
+                    "frac_issued_of_int8_peak_derived": issued_ops / (k_ms * 1e-3) / 1e12 / (2.0 * peaks["bf16_tflops"]),
+                    "quantize_kernel": {"ms": q_ms, "alg_bytes": 10.0 * f * n, "gbs": 10.0 * f * n / (q_ms * 1e-3) / 1e9,
+                                        "frac_hbm": 10.0 * f * n / (q_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                        "note": "4 bytes read + 6 bytes of digit planes written per value (HBM-bound)"},
+                    "call_ms": cov_s * 1e3,
+                    "traffic": TRAFFIC.get((engine, n, f)),
+                    "traffic_note": "dram bytes read + written per launch of this kernel from the committed ncu --set full "
+                                    "capture of this shape (profiles/); algorithmic bytes of the whole covariance pass = "
+                                    "4*F*n = %.3g" % (4.0 * f * n)}
+    else:
+        f16_kind = engine == "tc_3xf16"
+        tf32_peak = peaks["bf16_tflops_sustained"] if f16_kind else peaks["bf16_tflops_sustained"] / 2.0
+        burst_peak = peaks["bf16_tflops"] if f16_kind else peaks["bf16_tflops"] / 2.0
+        achieved = alg_flops / cov_s / 1e12
+        issued_mult = {"tc_3xf16": 3.0, "tc_3xtf32": 3.0, "tc_1xtf32": 1.0, "simt_f32": 1.0}[engine]
+        roofline = {"bound": "tensor", "kernel": f"cov_lag ({engine})", "achieved": achieved, "peak": tf32_peak,
+                    "unit": "TFLOP/s", "frac": achieved / tf32_peak, "traffic": TRAFFIC.get((engine, n, f)),
+                    "traffic_note": "bytes/launch (ncu); algorithmic bytes/launch = 4*F*n = %.3g" % (4.0 * f * n),
+                    "issued_tflops": achieved * issued_mult, "frac_issued": achieved * issued_mult / tf32_peak,
+                    "kernel_ms": cov_s * 1e3, "share_of_step": cov_s * 1e3 / ms_per_step,
+                    "peak_source": (f"{peaks['source']} bf16 sustained (kind::f16; kernel timed inside a long step)" if f16_kind else
+                                    f"{peaks['source']} bf16 sustained / 2 (TF32 : bf16 = 1 : 2 on tcgen05)"),
+                    "peak_burst": burst_peak, "frac_issued_of_burst": achieved * issued_mult / burst_peak,
+                    "algorithmic": "3*F^2 FLOP per frame pair; issued = x3 for the split-precision engines"}
 
     # ---- per-pass device times and the HBM fractions of the memory-bound passes (SURVEY 8d bytes)
     def _avg_ms(name):
@@ -641,15 +692,19 @@ def main():
         if numa_note:
             e2e["host_buffer"] = numa_note
 
+    _log("C2 timed region + e2e done")
     parity = None
     if rank == 0 and not args.no_parity:
         parity = parity_block(X, LAG, DIM, engine)
+        _log("parity block done")
     c3 = c5 = None
     if not args.no_legs:
         del buf, X
         torch.cuda.empty_cache()
         c5 = run_c5_leg(args, dev, rank, world, shards, peaks)
+        _log("C5 leg done")
         c3 = run_c3_leg(args, dev, rank, world, shards, peaks)
+        _log("C3 leg done")
 
     if rank == 0:
         cpu_baseline = None
@@ -658,7 +713,8 @@ def main():
         line = {"metric": "frames/s, TICA C0/Ctau + projection + KMeans (hot path)", "value": value,
                 "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": {"tc_3xf16": "f32 (f16x3 split-precision tensor contraction, f64 accumulation)",
+                "dtype": {"tc_i8x3": "f32 inputs; 23-bit fixed point in three int8 digit planes, exact int32 tensor-core accumulation, f64 results",
+                          "tc_3xf16": "f32 (f16x3 split-precision tensor contraction, f64 accumulation)",
                           "tc_3xtf32": "f32 (tf32x3 split-precision tensor contraction, f64 accumulation)"}.get(engine, "f32"),
                 "data": "synthetic", "config": workload_config(args, world, engine),
                 "roofline": roofline, "passes": passes, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,

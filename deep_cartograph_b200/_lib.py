@@ -19,8 +19,9 @@ COV_SIMT_F32 = 0
 COV_TC_3XTF32 = 1
 COV_TC_1XTF32 = 2
 COV_TC_3XF16 = 3
+COV_TC_I8X3 = 4
 COV_ENGINES = {"simt_f32": COV_SIMT_F32, "tc_3xtf32": COV_TC_3XTF32, "tc_1xtf32": COV_TC_1XTF32,
-               "tc_3xf16": COV_TC_3XF16}
+               "tc_3xf16": COV_TC_3XF16, "tc_i8x3": COV_TC_I8X3}
 
 _SIGNATURES = {
     # name: (restype, [argtypes])
@@ -34,6 +35,11 @@ _SIGNATURES = {
     "dcg_cov_workspace_bytes": (_c_sz, [_c_i64, _c_int, _c_int, _c_int, _c_int]),
     "dcg_cov_lag_f32": (_c_int, [_p, _c_i64, _c_int, _c_i64, _c_int, _p, _p, _c_int,
                                  _p, _p, _p, _p, _c_int, _p, _c_sz, _p]),
+    "dcg_cov_i8_workspace_bytes": (_c_sz, [_c_i64, _c_int, _c_int, _c_int]),
+    "dcg_cov_lag_i8_f32": (_c_int, [_p, _c_i64, _c_int, _c_i64, _c_int, _p, _p, _p, _p, _c_int,
+                                    _p, _p, _p, _p, _p, _p, _c_sz, _p]),
+    "dcg_cov_i8_set_timing": (_c_int, [_c_int]),
+    "dcg_cov_i8_get_timing": (_c_int, [C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(_c_int)]),
     "dcg_project_workspace_bytes": (_c_sz, [_c_i64, _c_int, _c_int]),
     "dcg_project_f32": (_c_int, [_p, _c_i64, _c_int, _c_i64, _p, _p, _p, _c_int, _p, _p, _p,
                                  _p, _c_sz, _p]),

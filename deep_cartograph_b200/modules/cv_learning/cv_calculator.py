@@ -196,10 +196,16 @@ class CVCalculator:
         ld = (f_in + 3) // 4 * 4
         aligned = (X.device == dev and X.dim() == 2 and X.stride(1) == 1 and X.stride(0) % 4 == 0
                    and X.data_ptr() % 16 == 0)
+        # a resident shard that is the leading view of a buffer with `lag` spare rows receives its halo
+        # in place (FrameShards.with_halo): no copy (at C3 a shard is up to 99 GB)
+        base = X._base
+        room = (halo == 0 or (base is not None and base.dim() == 2 and base.stride(1) == 1
+                              and base.stride(0) == X.stride(0) and base.data_ptr() == X.data_ptr()
+                              and base.shape[0] >= n_in + halo and base.shape[1] >= f_in))
         self.shards = shards
         self._spec = None
         st = None
-        if halo or not aligned:
+        if not (aligned and room):
             # HBM layout: rows padded to a multiple of 4 floats so every row starts 16-byte aligned
             # (16-byte loads in every kernel; e.g. 4950 features -> row stride 4952), plus spare rows
             # after the shard so the lag halo is received in place (no second copy)
@@ -233,6 +239,7 @@ class CVCalculator:
         }
         self.features_norm_mean, self.features_norm_range = self.prepare_normalization()
         self._dev_norm = None
+        self._dev_bounds = None
 
     # ---- host -> device streaming with speculative sums ------------------------------------------
     def _sums_plan(self):
@@ -287,6 +294,7 @@ class CVCalculator:
                 e.record(copier)
                 events.append(e)
         parts, acc, norm0, start = [], None, None, 0
+        lo = hi = None
         engine = self.backend.get("cov_engine")
         if plan is not None and self.feats_norm_mode is not None:
             # provisional parameters: statistics of ~2048 evenly spaced rows, taken on the host before
@@ -308,8 +316,13 @@ class CVCalculator:
             lag, block, want_st = plan
             if c1 - start <= lag:
                 continue
+            # column bounds of every row seen so far (a superset of this chunk's rows)
+            lo = parts[-1]["min"] if lo is None else torch.minimum(lo, parts[-1]["min"])
+            hi = parts[-1]["max"] if hi is None else torch.maximum(hi, parts[-1]["max"])
             s = ops.lagged_covariance(data[start:c1], lag, norm0[0] if norm0 else None,
-                                      norm0[1] if norm0 else None, block=block, engine=engine, want_st=want_st)
+                                      norm0[1] if norm0 else None, block=block, engine=engine, want_st=want_st,
+                                      xmin=lo, xmax=hi)
+            s.pop("clamped", None)
             if acc is None:
                 acc = s
             else:
@@ -352,6 +365,15 @@ class CVCalculator:
             self._dev_norm = (torch.tensor(self.features_norm_mean, dtype=torch.float32, device=dev),
                               torch.tensor(self.features_norm_range, dtype=torch.float32, device=dev))
         return self._dev_norm
+
+    def _bounds_on_device(self):
+        """(min, max) of every feature over ALL frames (all shards): the column bounds the exact integer
+        covariance engine scales its fixed point by."""
+        if getattr(self, "_dev_bounds", None) is None:
+            dev = self.training_data.device
+            self._dev_bounds = (torch.tensor(self.features_stats["min"], dtype=torch.float32, device=dev),
+                                torch.tensor(self.features_stats["max"], dtype=torch.float32, device=dev))
+        return self._dev_bounds
 
     def standardized_training_data(self) -> torch.Tensor:
         """The tensor the reference holds in ``training_data`` after load (:799-804)."""
@@ -536,7 +558,10 @@ class LinearCalculator(CVCalculator):
         engine = self.backend.get("cov_engine")
         s = self._take_speculative_sums(X, lag, block, want_st, mean, rng, engine)
         if s is None:
-            s = ops.lagged_covariance(X, lag, mean, rng, block=block, engine=engine, want_st=want_st)
+            xmin, xmax = self._bounds_on_device()
+            s = ops.lagged_covariance(X, lag, mean, rng, block=block, engine=engine, want_st=want_st,
+                                      xmin=xmin, xmax=xmax)
+        s.pop("clamped", None)
         if self.shards is not None:
             s = self.shards.allreduce_sums(s, m_total=(self.num_frames - lag) if self.num_frames else None)
         # ALWAYS rebuild the lower triangle from the upper one after the reduction: a rank that kept
@@ -572,6 +597,7 @@ class LinearCalculator(CVCalculator):
         done = spec["rows_done"]                               # pairs t < done - lag are in `s`
         if X.shape[0] > done:                                  # lag halo of the next shard arrived since
             t = ops.lagged_covariance(X[done - lag:], lag, m0, r0, block=block, engine=engine, want_st=want_st)
+            t.pop("clamped", None)
             for k in ("S0", "St", "a", "b"):
                 if t.get(k) is not None:
                     s[k] += t[k]
@@ -706,6 +732,7 @@ class HTICACalculator(LinearCalculator):
         if self.shards is not None:
             P = self.shards.with_halo(P, lag)
         s = ops.lagged_covariance(P, lag, engine=self.backend.get("cov_engine"))
+        s.pop("clamped", None)
         if self.shards is not None:
             s = self.shards.allreduce_sums(s)
         S0 = ops.symmetrize_upper(s["S0"])

@@ -66,12 +66,13 @@ def _ws(nbytes: int, device) -> torch.Tensor:
 
 
 def default_cov_engine(standardised: bool = True) -> int:
-    """Engine used when none is requested: env DCG_COV_ENGINE, else the tcgen05 split-precision
-    engine -- 3xF16 when the kernel standardises the data itself (|z| is then far inside the FP16
-    range; same 11-bit pieces as 3xTF32 at half the MMA count), 3xTF32 for raw inputs."""
+    """Engine used when none is requested: env DCG_COV_ENGINE, else the exact integer tensor-core
+    engine (``tc_i8x3``: 23-bit fixed point per column, int32 accumulation -- the only fast engine
+    that holds the 1e-5 eigenvector tolerance at the C2 eigenvalue gaps).  The float
+    engines stay selectable: ``tc_3xf16`` needs standardised inputs (|z| < 65504), ``tc_3xtf32`` does not."""
     name = os.environ.get("DCG_COV_ENGINE", "auto")
     if name == "auto":
-        return COV_ENGINES["tc_3xf16" if standardised else "tc_3xtf32"]
+        return COV_ENGINES["tc_i8x3"]
     if name not in COV_ENGINES:
         raise ValueError(f"DCG_COV_ENGINE={name!r}; choose from {sorted(COV_ENGINES)} or 'auto'")
     return COV_ENGINES[name]
@@ -150,11 +151,15 @@ def standardize_(X: torch.Tensor, mean: torch.Tensor, rng: torch.Tensor) -> torc
 # ---- A5/A6/A7/A8 ------------------------------------------------------------------------------
 def lagged_covariance(X: torch.Tensor, lag: int, mean: Optional[torch.Tensor] = None,
                       rng: Optional[torch.Tensor] = None, block: int = 0, engine=None,
-                      want_s0: bool = True, want_st: bool = True) -> dict:
+                      want_s0: bool = True, want_st: bool = True,
+                      xmin: Optional[torch.Tensor] = None, xmax: Optional[torch.Tensor] = None) -> dict:
     """Raw FP64 sums over the M = n_rows - lag pairs of the (optionally standardised) rows:
     S0 = sum z_t z_t^T (upper triangle valid), St = sum z_t z_{t+lag}^T, a = sum_{t<M} z_t,
     b = sum_{t>=lag} z_t.  Replaces create_timelagged_dataset + TICA.compute's correlation
-    sums (reference cv_calculator.py:2244-2261)."""
+    sums (reference cv_calculator.py:2244-2261).
+
+    ``xmin`` / ``xmax`` (per-column bounds of X, float32) are used by the exact integer engine
+    (``tc_i8x3``); when absent they are taken from X here (one more pass over X)."""
     _need_cuda("X", X, torch.float32)
     n, f, ld = _rows("X", X)
     if not (0 <= lag < n):
@@ -174,12 +179,37 @@ def lagged_covariance(X: torch.Tensor, lag: int, mean: Optional[torch.Tensor] = 
     St = torch.empty((f, f), dtype=torch.float64, device=dev) if want_st else None
     a = torch.empty(f, dtype=torch.float64, device=dev)
     b = torch.empty(f, dtype=torch.float64, device=dev)
+    if eng == _lib.COV_TC_I8X3:
+        if xmin is None or xmax is None:
+            xmin, xmax = X.amin(dim=0), X.amax(dim=0)
+        _need_cuda("xmin", xmin, torch.float32)
+        _need_cuda("xmax", xmax, torch.float32)
+        info = torch.empty(1, dtype=torch.int32, device=dev)
+        ws = _ws(lib.dcg_cov_i8_workspace_bytes(n, f, lag, block), dev)
+        _call(X.device, "dcg_cov_lag_i8_f32", X.data_ptr(), n, f, ld, lag, _ptr(mean), _ptr(rng),
+              xmin.contiguous().data_ptr(), xmax.contiguous().data_ptr(), block, _ptr(S0), _ptr(St),
+              a.data_ptr(), b.data_ptr(), info.data_ptr(), ws.data_ptr(), ws.numel(), _stream(X.device))
+        _count(5)                                      # prep + plan + quantise + contraction + column sums (per window)
+        return {"S0": S0, "St": St, "a": a, "b": b, "M": n - lag, "clamped": info}
     ws = _ws(lib.dcg_cov_workspace_bytes(n, f, lag, block, eng), dev)
     _call(X.device, "dcg_cov_lag_f32", X.data_ptr(), n, f, ld, lag, _ptr(mean), _ptr(rng), block,
               _ptr(S0), _ptr(St), a.data_ptr(), b.data_ptr(), eng, ws.data_ptr(), ws.numel(),
               _stream(X.device))
     _count(2 if eng == _lib.COV_SIMT_F32 else 3)      # colsum + engine (+ split reduction)
     return {"S0": S0, "St": St, "a": a, "b": b, "M": n - lag}
+
+
+def cov_i8_timing(on: Optional[bool] = None):
+    """Switch the exact engine's kernel timing on / off, or (``on`` None) read and reset it:
+    returns dict(quantize_ms, contract_ms, launches) summed since the last read."""
+    import ctypes
+    lib = _lib.load()
+    if on is not None:
+        _lib.check("dcg_cov_i8_set_timing", lib.dcg_cov_i8_set_timing(1 if on else 0))
+        return None
+    q, c, n = ctypes.c_float(), ctypes.c_float(), ctypes.c_int()
+    _lib.check("dcg_cov_i8_get_timing", lib.dcg_cov_i8_get_timing(ctypes.byref(q), ctypes.byref(c), ctypes.byref(n)))
+    return {"quantize_ms": q.value, "contract_ms": c.value, "launches": n.value}
 
 
 def symmetrize_upper(S: torch.Tensor) -> torch.Tensor:

@@ -94,6 +94,30 @@ int dcg_cov_lag_f32(const float* X, int64_t n_rows, int f, int64_t ld, int lag,
                     double* S0, double* St, double* colsum_t, double* colsum_lag,
                     int engine, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- A5/A6/A7/A8, exact engine: integer tensor cores ---------------------------------------------
+ * Same sums as dcg_cov_lag_f32 (same reference call sites), computed EXACTLY on the int8 tensor
+ * cores (tcgen05 kind::i8, int32 accumulation): every value is first rounded to 24-bit fixed point
+ * relative to its column's range, q = rint((x - mean[j]) * 2^e_j) -- the float32 resolution of the
+ * data -- split into three int8 digit planes in the K-major layout of the contraction (one HBM-bound
+ * pass), and the planes are contracted by TMA-staged integer MMAs; nothing is rounded afterwards
+ * (csrc/cov_i8.cu).  `xmin` / `xmax` (f, float32, device): per-column bounds of X over ALL n_rows rows
+ * (the column statistics, dcg_colstats_f32); values outside them are clamped and counted in
+ * `info[0]` (int32, device, may be NULL).  The digit planes of a window of frames live in `ws`.     */
+#define DCG_COV_TC_I8X3    4 /* tcgen05 kind::i8 on three int8 digit planes: exact accumulation    */
+size_t dcg_cov_i8_workspace_bytes(int64_t n_rows, int f, int lag, int block);
+int dcg_cov_lag_i8_f32(const float* X, int64_t n_rows, int f, int64_t ld, int lag,
+                       const float* mean, const float* range, const float* xmin, const float* xmax,
+                       int block, double* S0, double* St, double* colsum_t, double* colsum_lag,
+                       int* info, void* ws, size_t ws_bytes, void* stream);
+
+/* Device timing of the exact engine's two kernels (diagnostics for bench.py's roofline): when switched
+ * on, every window's quantise and contraction launches are bracketed by CUDA events on the launching
+ * stream (up to 64 windows between reads); dcg_cov_i8_get_timing synchronises on them and returns the
+ * summed durations in ms and the number of contraction launches since the last read.  One stream, one
+ * host thread.                                                                                        */
+int dcg_cov_i8_set_timing(int on);
+int dcg_cov_i8_get_timing(float* quantize_ms, float* contract_ms, int* launches);
+
 /* ---- A9/A10: projection ----------------------------------------------------------------------
  * Replaces `LinearCalculator.normalize_cv` + `project_data` (cv_calculator.py:918-991):
  * P[t,:] = ((x_t - mean)/range) @ W  (mean/range NULL: no standardisation), W is f x d row-major
