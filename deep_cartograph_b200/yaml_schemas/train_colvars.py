@@ -20,9 +20,9 @@ class InputColvars(BaseModel):
 class Backend(BaseModel):
     """B200 backend options (not in the reference)."""
     model_config = ConfigDict(extra="allow")
-    # covariance contraction engine: auto (tcgen05 3xF16 on standardised data, 3xTF32 on raw data),
-    # or one of the tcgen05 engines / the CUDA-core FP32 engine explicitly
-    cov_engine: Literal["auto", "tc_3xf16", "tc_3xtf32", "tc_1xtf32", "simt_f32"] = "auto"
+    # covariance contraction engine: auto (= tc_i8x3, the exact integer tensor-core engine), or one of
+    # the float tcgen05 engines / the CUDA-core FP32 engine explicitly
+    cov_engine: Literal["auto", "tc_i8x3", "tc_3xf16", "tc_3xtf32", "tc_1xtf32", "simt_f32"] = "auto"
     # hTICA: accumulate the full F x F Gram in one pass when F <= this, else block-diagonal + 2nd pass
     htica_full_gram_max_features: int = 2048
     # CUDA device index (None = current device / LOCAL_RANK)
