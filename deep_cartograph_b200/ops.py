@@ -518,3 +518,40 @@ def gen_eig_small(H: torch.Tensor, G: torch.Tensor):
               status.data_ptr(), _stream(H.device))
     _count(1)
     return theta, S, status
+
+
+# ---- N4: free-energy surface (binned KDE) ---------------------------------------------------------
+def fes_density(P: torch.Tensor, cols, bounds, num_bins: int, bandwidth: float, blocks: int = 1):
+    """Binned Gaussian KDE of the projected frames on an equidistant grid, per block of frames
+    (what mlcolvar's ``compute_fes(backend="KDEpy")`` evaluates, reference modules/figures/figures.py:95).
+
+    ``P``: (n, d) float32 CUDA tensor; ``cols``: one or two column indices; ``bounds``: (lo, hi) or
+    [(lo, hi), (lo, hi)].  Returns (density (blocks, G) or (blocks, G, G) [iy, ix] FP64, frames per block
+    (blocks,) FP64, number of frames outside the bounds)."""
+    _need_cuda("P", P, torch.float32)
+    n, d, ld = _rows("P", P)
+    cols = [int(c) for c in (cols if isinstance(cols, (list, tuple)) else [cols])]
+    if len(cols) not in (1, 2) or any(not 0 <= c < d for c in cols):
+        raise ValueError("cols must be one or two column indices of P")
+    dim = len(cols)
+    b = [tuple(map(float, bounds))] if dim == 1 else [tuple(map(float, x)) for x in bounds]
+    G = int(num_bins)
+    blocks = int(blocks)
+    if not 1 <= blocks <= n:
+        raise ValueError("1 <= blocks <= number of frames")
+    dev = P.device
+    shape = (blocks, G) if dim == 1 else (blocks, G, G)
+    hist = torch.empty(shape, dtype=torch.float64, device=dev)
+    outside = torch.empty(1, dtype=torch.int64, device=dev)
+    (lo0, hi0), (lo1, hi1) = b[0], (b[1] if dim == 2 else (0.0, 1.0))
+    _call(dev, "dcg_fes_bin_f32", P.data_ptr(), n, ld, cols[0], cols[1] if dim == 2 else -1, lo0, hi0, lo1, hi1,
+          G, blocks, hist.data_ptr(), outside.data_ptr(), _stream(dev))
+    q, r = divmod(n, blocks)
+    frames = torch.tensor([q + 1] * r + [q] * (blocks - r), dtype=torch.float64, device=dev)
+    dens = torch.empty_like(hist)
+    tmp = torch.empty_like(hist) if dim == 2 else None
+    _call(dev, "dcg_fes_smooth_f64", hist.data_ptr(), blocks, G, dim, (hi0 - lo0) / (G - 1),
+          (hi1 - lo1) / (G - 1) if dim == 2 else 1.0, float(bandwidth), frames.data_ptr(), dens.data_ptr(),
+          _ptr(tmp), _stream(dev))
+    _count(2 if dim == 1 else 3)
+    return dens, frames, outside

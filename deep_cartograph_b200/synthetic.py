@@ -14,7 +14,20 @@ import numpy as np
 import torch
 
 
+_CHAINS = {}
+
+
 def latent_chains(n_total: int, n_slow: int, seed: int = 0, t0: float = 4000.0) -> np.ndarray:
+    """(n_total x n_slow) latent AR(1) chains; the last result is cached (callers generate a shard in
+    row chunks, and the whole-series filter costs seconds at 10M frames)."""
+    key = (n_total, n_slow, seed, t0)
+    if key not in _CHAINS:
+        _CHAINS.clear()
+        _CHAINS[key] = _latent_chains(n_total, n_slow, seed, t0)
+    return _CHAINS[key]
+
+
+def _latent_chains(n_total: int, n_slow: int, seed: int = 0, t0: float = 4000.0) -> np.ndarray:
     from scipy.signal import lfilter
     rng = np.random.default_rng(seed)
     T = t0 * 2.0 ** (-np.arange(n_slow))

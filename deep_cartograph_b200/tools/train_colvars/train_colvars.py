@@ -2,8 +2,10 @@
 
 Same signature, return value and on-disk layout as the reference's
 ``tools/train_colvars/train_colvars.py:20-155`` / ``train_colvars_workflow.py:24-411`` for the
-CVs of the hot path (pca, tica, htica).  FES / plots / PLUMED input export / sensitivity
-analysis are outside the hot path and are not produced.
+CVs of the hot path (pca, tica, htica, deep_tica).  The free-energy surfaces of the projection
+(reference train_colvars_workflow.py:146-182) are computed on the device and saved as ``fes*.npy``
+(no figure is drawn: matplotlib is not part of this image); plots, PLUMED input
+export and sensitivity analysis are outside the hot path.
 """
 from __future__ import annotations
 
@@ -15,7 +17,8 @@ from pathlib import Path
 from typing import Dict, List, Optional, Union
 
 from ...modules.common import files_exist, merge_configurations, validate_configuration
-from ...modules.cv_learning.cv_calculator import cv_calculators_map
+from ...modules.cv_learning.cv_calculator import cv_calculators_map, cv_names_map
+from ...modules.figures import figures
 from ...yaml_schemas.train_colvars import TrainColvarsSchema
 
 logger = logging.getLogger(__name__)
@@ -68,6 +71,22 @@ class TrainColvarsWorkflow:
         return all(files_exist(self.get_output_cv_model_path(cv)) and
                    files_exist(*self.get_output_cv_trajectories(cv)) for cv in self.cvs_list)
 
+    def create_fes_plots(self, data, cv_name: str, cv_labels: List[str], output_folder: str):
+        """Reference ``create_fes_plots`` (train_colvars_workflow.py:146-182): one 1-D FES per CV
+        component with 100 blocks, one 2-D FES per pair of components with 1 block."""
+        import numpy as np
+        settings = (self.configuration.get("figures") or {}).get("fes") or {}
+        cv_type = cv_names_map.get(cv_name, cv_name)
+        X = data.to_numpy(dtype=np.float32)
+        d = X.shape[1]
+        for i in range(d):
+            figures.plot_fes(X[:, i], [cv_labels[i]], settings,
+                             os.path.join(output_folder, f"fes_{cv_type}_{i + 1}"), num_blocks=100)
+        for i in range(d - 1):
+            for j in range(i + 1, d):
+                figures.plot_fes(X[:, [i, j]], [cv_labels[i], cv_labels[j]], settings,
+                                 os.path.join(output_folder, f"fes_{cv_type}_{i + 1}_{j + 1}"), num_blocks=1)
+
     def run(self) -> Dict:
         if self.workflow_finished():
             logger.info("Skipping collective variable computation.")
@@ -96,6 +115,8 @@ class TrainColvarsWorkflow:
                 os.makedirs(out, exist_ok=True)
                 df_i = projected[projected["traj_label"] == traj_index].drop("traj_label", axis=1)
                 df_i.to_csv(os.path.join(out, "projected_trajectory.csv"), index=False, float_format="%.4f")
+                if ((self.configuration.get("figures") or {}).get("fes") or {}).get("compute", False):
+                    self.create_fes_plots(df_i, cv_name, calc.get_labels(), out)
         return self.get_output_paths()
 
 

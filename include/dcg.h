@@ -231,6 +231,25 @@ int dcg_ticaloss_f64(const double* sums, int d, double reg, int n_eig, double* r
 int dcg_gen_eig_small_f64(const double* H, const double* G, int b, int batch,
                           double* theta, double* S, double* status, void* stream);
 
+/* ---- N4: free-energy surface by binned kernel density estimation ---------------------------------
+ * Replaces mlcolvar.utils.fes.compute_fes(backend="KDEpy") as called at modules/figures/figures.py:95
+ * (from tools/train_colvars/train_colvars_workflow.py:146-182).  KDEpy's FFTKDE = linear binning onto
+ * the evaluation grid + convolution with the sampled kernel:
+ *   dcg_fes_bin_f32    P is n x ld float32 (the projected frames); column c0 is x, column c1 is y
+ *                      (c1 < 0: 1-D).  Frames are split into `blocks` contiguous blocks
+ *                      (numpy.array_split); block b's linear-binning weights land in
+ *                      hist[b][iy][ix] (FP64, G x G or G nodes spanning [lo, hi] per axis, overwritten).
+ *                      Frames outside the bounds are skipped and counted in *n_outside (device, may be NULL).
+ *   dcg_fes_smooth_f64 density[b] = (hist[b] / block_frames[b]) convolved with a Gaussian of standard
+ *                      deviation `bandwidth` sampled at the grid offsets (step0, step1 = grid spacing);
+ *                      block_frames NULL: no normalisation.  tmp: blocks*G*G doubles (dim 2 only).     */
+int dcg_fes_bin_f32(const float* P, int64_t n, int64_t ld, int c0, int c1,
+                    double lo0, double hi0, double lo1, double hi1, int G, int blocks,
+                    double* hist, int64_t* n_outside, void* stream);
+int dcg_fes_smooth_f64(const double* hist, int blocks, int G, int dim, double step0, double step1,
+                       double bandwidth, const double* block_frames, double* density, double* tmp,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -116,6 +116,19 @@ def main():
         km[f"{name}_labels"] = labels.astype(np.int32)
         km[f"{name}_centers"] = centers
     np.savez_compressed(os.path.join(HERE, "kmeans_ref.npz"), **km)
+
+    # ---- FES: the reference's own legacy output (mlcolvar compute_fes through KDEpy; bandwidth 0.025,
+    # 200 bins, 300 K: data/calpha_transitions/input/distances_config.yml:93-95) and the projected
+    # trajectory it was computed from
+    import pandas as pd
+    base = os.path.join(REF, "deep_cartograph", "data", "calpha_transitions", "reference", "1rcs_B-3ssx_R-3",
+                        "train_colvars", "pca")
+    d = pd.read_csv(os.path.join(base, "projected_trajectory.csv"))
+    np.savez_compressed(os.path.join(HERE, "fes_legacy_pca.npz"), X=d[["PC 1", "PC 2"]].to_numpy(),
+                        fes=np.load(os.path.join(base, "fes", "fes.npy")).astype(np.float32),
+                        grid=np.load(os.path.join(base, "fes", "grid.npy")),
+                        bounds=np.load(os.path.join(base, "fes", "bounds.npy")),
+                        bandwidth=0.025, num_bins=200, temperature=300)
     print("wrote", os.listdir(HERE))
 
 

@@ -1114,3 +1114,80 @@ def test_ops_reject_cpu_tensors():
     from deep_cartograph_b200 import ops
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ops.column_stats(torch.zeros(4, 4))
+
+
+# ------------------------------------------------------------------------------------------------
+# N4 free-energy surface (binned KDE)
+# ------------------------------------------------------------------------------------------------
+def test_fes_matches_reference_legacy_output_and_oracle(dev):
+    """compute_fes on the device == the numpy restatement == the FES the reference wrote for its
+    calpha_transitions example (2-D, one block)."""
+    from deep_cartograph_b200.modules.figures import figures
+    from oracle import fes_oracle as fo
+    g = dict(np.load(os.path.join(GOLDEN, "fes_legacy_pca.npz")))
+    bounds = [tuple(b) for b in g["bounds"]]
+    fes, grid, b, err = figures.compute_fes(g["X"], temp=float(g["temperature"]), num_samples=int(g["num_bins"]),
+                                            bounds=bounds, bandwidth=float(g["bandwidth"]), blocks=1, eps=1e-10)
+    ref, rgrid, _, _ = fo.compute_fes(g["X"].astype(np.float32), 300, 200, bounds, 0.025, 1, 1e-10)
+    assert err is None
+    np.testing.assert_allclose(np.asarray(grid), np.asarray(rgrid), atol=1e-12)
+    low = ref < 25
+    assert np.abs(fes - ref)[low].max() < 1e-4            # same algorithm: float32 binning weights only
+    assert np.abs(fes - g["fes"])[g["fes"] < 20].max() < 2e-3
+
+
+@pytest.mark.parametrize("n,blocks,bins", [(25_000, 100, 150), (9_999, 7, 64), (1_000_003, 100, 150)])
+def test_fes_1d_block_average_matches_oracle(dev, n, blocks, bins):
+    from deep_cartograph_b200.modules.figures import figures
+    from oracle import fes_oracle as fo
+    rng = np.random.default_rng(n)
+    x = np.concatenate([rng.normal(-0.5, 0.1, n // 3), rng.normal(0.4, 0.2, n - n // 3)]).astype(np.float32)
+    rng.shuffle(x)
+    P = torch.zeros((n, 3), dtype=torch.float32, device=dev)
+    P[:, 1] = torch.from_numpy(x).to(dev)                      # a column of a wider projection
+    bounds = fo.get_ranges(x)
+    fes, grid, _, err = figures.compute_fes(P, num_samples=bins, bounds=bounds, bandwidth=0.05, blocks=blocks,
+                                            eps=1e-10, cols=[1])
+    ref, rgrid, _, rerr = fo.compute_fes(x, 300, bins, bounds, 0.05, blocks, 1e-10)
+    np.testing.assert_allclose(grid, rgrid, atol=1e-12)
+    core = ref < 20
+    assert np.abs(fes - ref)[core].max() < 2e-4
+    assert np.abs(err - rerr)[core].max() < 2e-4
+
+
+def test_fes_2d_large_and_outside_frames(dev):
+    """2-D FES of 4M frames against the oracle on a strided subsample's bounds (size-independent: the
+    density integrates to one), and frames outside the bounds are counted, not binned."""
+    from deep_cartograph_b200 import ops
+    from oracle import fes_oracle as fo
+    n = 4_000_000
+    g = torch.Generator(device=dev).manual_seed(1)
+    P = torch.randn((n, 4), generator=g, device=dev) * torch.tensor([0.3, 0.2, 1.0, 1.0], device=dev)
+    bounds = [(-1.2, 1.2), (-0.9, 0.9)]
+    dens, frames, outside = ops.fes_density(P, [0, 1], bounds, 150, 0.05, 1)
+    n_out = int(((P[:, 0].abs() > 1.2) | (P[:, 1].abs() > 0.9)).sum())
+    assert int(outside.item()) == n_out and n_out > 0
+    step = (2.4 / 149) * (1.8 / 149)
+    assert abs(float(dens.sum()) * step * n / (n - n_out) - 1.0) < 2e-3
+    sub = P[: 200_000, :2].cpu().numpy()
+    inside = (np.abs(sub[:, 0]) <= 1.2) & (np.abs(sub[:, 1]) <= 0.9)
+    ref = fo.binned_density(sub[inside], bounds, 150, 0.05)
+    d2, _, _ = ops.fes_density(torch.from_numpy(sub[inside]).to(dev), [0, 1], bounds, 150, 0.05, 1)
+    np.testing.assert_allclose(d2[0].cpu().numpy(), ref, rtol=2e-5, atol=1e-7)
+
+
+def test_train_colvars_writes_fes_files(dev, c1, tmp_path):
+    """Step API with figures.fes.compute: fes*.npy per component (100 blocks, reduced to 1 for 164
+    frames as the reference does) and per pair."""
+    from deep_cartograph_b200.tools.train_colvars.train_colvars import train_colvars
+    cfg = _config()
+    cfg["cvs"] = ["pca"]
+    cfg["figures"] = {"fes": {"compute": True, "save": True, "num_bins": 50, "bandwidth": 0.1}}
+    out = train_colvars(configuration=cfg, train_colvars_paths=[os.path.join(GOLDEN, "peptide_c1.dat")],
+                        features_list=list(np.loadtxt(os.path.join(GOLDEN, "peptide_c1_features.txt"), dtype=str)),
+                        dimension=2, output_folder=str(tmp_path))
+    base = os.path.dirname(out["pca"]["traj_paths"][0])
+    for sub, shape in (("fes_PCA_1", (50,)), ("fes_PCA_2", (50,)), ("fes_PCA_1_2", (50, 50))):
+        fes = np.load(os.path.join(base, sub, "fes.npy"))
+        assert fes.shape == shape and np.isfinite(fes).all() and fes.min() == 0.0
+        assert os.path.exists(os.path.join(base, sub, "fes_grid.npy"))

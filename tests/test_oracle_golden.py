@@ -232,3 +232,37 @@ def test_float64_device_checker_equals_numpy_oracle():
     cm, cr = oracle.cv_normalization(P)
     np.testing.assert_allclose(Pn.numpy(), (P - cm) / cr, atol=1e-7)
     assert f64.eigvec_error(V, -torch.from_numpy(V_o)) < 1e-8
+
+
+def test_fes_restatement_reproduces_the_reference_legacy_output():
+    """N4: oracle/fes_oracle.py (binned Gaussian KDE -> -kbT log) reproduces the FES the reference
+    itself wrote for the bundled calpha_transitions example (mlcolvar compute_fes through KDEpy,
+    bandwidth 0.025, 200 bins, 300 K) from the projected trajectory stored next to it."""
+    from oracle import fes_oracle as fo
+    g = dict(np.load(os.path.join(GOLDEN, "fes_legacy_pca.npz")))
+    fes, grid, bounds, err = fo.compute_fes(g["X"], float(g["temperature"]), int(g["num_bins"]),
+                                            [tuple(b) for b in g["bounds"]], float(g["bandwidth"]), 1, 1e-10)
+    assert err is None and fes.shape == g["fes"].shape
+    np.testing.assert_allclose(np.asarray(grid), g["grid"], atol=1e-12)
+    low = g["fes"] < 20                      # KDEpy truncates the kernel where the density is negligible
+    assert np.abs(fes - g["fes"])[low].max() < 2e-3
+    assert np.unravel_index(fes.argmin(), fes.shape) == np.unravel_index(g["fes"].argmin(), g["fes"].shape)
+    # the legacy bounds are the data range +/- 5 % (today's get_ranges uses 0.5 %, figures.py:441)
+    lo, hi = g["X"].min(0), g["X"].max(0)
+    np.testing.assert_allclose(g["bounds"], np.stack([lo - 0.05 * (hi - lo), hi + 0.05 * (hi - lo)], 1), rtol=1e-9)
+
+
+def test_fes_block_average_properties():
+    from oracle import fes_oracle as fo
+    rng = np.random.default_rng(3)
+    x = np.concatenate([rng.normal(-0.5, 0.1, 4000), rng.normal(0.4, 0.2, 6000)])
+    rng.shuffle(x)
+    fes1, grid, b, e1 = fo.compute_fes(x, 300, 150, fo.get_ranges(x), 0.05, 1, 1e-10)
+    fesb, _, _, eb = fo.compute_fes(x, 300, 150, fo.get_ranges(x), 0.05, 100, 1e-10)
+    assert e1 is None and eb.shape == fesb.shape == (150,)
+    core = fes1 < 3                                       # well-sampled region (100 frames per block:
+    assert np.abs(fesb - fes1)[core].max() < 1.0          # averaging -log of noisy densities is biased in the tails)
+    assert (eb[core] < 0.5).all() and (eb >= 0).all()
+    # density integrates to one on the grid
+    dens = fo.binned_density(x, b, 150, 0.05)
+    assert abs(np.trapezoid(dens, grid) - 1.0) < 1e-3
