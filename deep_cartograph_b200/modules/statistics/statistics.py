@@ -49,29 +49,35 @@ def _to_device(features) -> torch.Tensor:
     return t.to(_device()).contiguous()
 
 
-def _kmeanspp_init(Y: torch.Tensor, k: int, seed: int) -> torch.Tensor:
-    """k-means++ seeding (greedy variant as in sklearn _kmeans_plusplus) on the device with a
-    seeded torch generator.  NOT bit-identical to numpy's RandomState stream: parity with the
-    reference is defined for fixed initial centroids (BASELINE.json north_star)."""
-    n, d = Y.shape
-    gen = torch.Generator(device=Y.device)
-    gen.manual_seed(seed)
-    Yd = Y.to(torch.float64)
+def _kmeanspp_sklearn(Yc: torch.Tensor, k: int, rs: np.random.RandomState) -> torch.Tensor:
+    """scikit-learn's greedy k-means++ (sklearn/cluster/_kmeans.py ``_kmeans_plusplus``, reached from
+    reference statistics.py:189-195 with ``init='k-means++'``, ``random_state=0``) on the CENTRED frames
+    ``Yc`` (KMeans.fit centres X first, _kmeans.py:1486-1493): the random draws come from the SAME numpy
+    ``RandomState`` stream (first centre: ``choice(n, p=uniform)``; then ``2 + int(log k)`` uniform
+    draws per centre against the cumulative D^2 potential), the O(n k) distance work runs on the device
+    in FP64.  The centres equal scikit-learn's unless a draw lands within rounding of a cumulative-sum
+    boundary."""
+    n, d = Yc.shape
+    Yd = Yc.to(torch.float64)
     n_trials = 2 + int(np.log(k))
-    centers = torch.empty((k, d), dtype=torch.float64, device=Y.device)
-    first = int(torch.randint(n, (1,), generator=gen, device=Y.device).item())
+    centers = torch.empty((k, d), dtype=torch.float64, device=Yc.device)
+    if n <= 5_000_000:
+        first = int(rs.choice(n, p=np.full(n, 1.0 / n)))
+    else:      # the same draw without the n-vector: choice() searches u in cdf_i = (i + 1) / n -> floor(u n)
+        first = min(n - 1, int(np.floor(rs.random_sample() * n)))
     centers[0] = Yd[first]
     closest = ((Yd - centers[0]) ** 2).sum(dim=1)
+    pot = float(closest.sum().item())
     for c in range(1, k):
-        pot = closest.sum()
-        r = torch.rand(n_trials, generator=gen, device=Y.device, dtype=torch.float64) * pot
-        cand = torch.searchsorted(torch.cumsum(closest, 0), r).clamp_(max=n - 1)
-        dist = ((Yd[cand][:, None, :] - Yd[None, :, :]) ** 2).sum(dim=2) if n * n_trials * d < 5e8 else \
-            torch.stack([((Yd - Yd[i]) ** 2).sum(dim=1) for i in cand])
+        rand_vals = torch.from_numpy(rs.uniform(size=n_trials) * pot).to(Yc.device)
+        cand = torch.searchsorted(torch.cumsum(closest, 0), rand_vals).clamp_(max=n - 1)
+        dist = torch.stack([((Yd - Yd[i]) ** 2).sum(dim=1) for i in cand])
         dist = torch.minimum(dist, closest[None, :])
-        best = int(torch.argmin(dist.sum(dim=1)).item())
-        centers[c] = Yd[cand[best]]
+        pots = dist.sum(dim=1)
+        best = int(torch.argmin(pots).item())
+        pot = float(pots[best].item())
         closest = dist[best]
+        centers[c] = Yd[cand[best]]
     return centers
 
 
@@ -202,9 +208,11 @@ def _relocate_empty(Yc, C, labels, sums, counts, empty, shards):
 
 def kmeans_clustering(feature_matrix, num_clusters: int, n_init: int,
                       initial_centroids=None) -> Tuple[np.ndarray, np.ndarray]:
-    """Reference statistics.py:159-197.  With ``initial_centroids`` the number of clusters comes
-    from their shape and a single run is made (as sklearn does for an ndarray init); otherwise
-    ``n_init`` k-means++ seedings (seed 0, 1, ...) and the lowest inertia wins."""
+    """Reference statistics.py:159-197: ``KMeans(n_clusters, random_state=0, init, n_init).fit_predict``.
+    With ``initial_centroids`` the number of clusters comes from their shape and a single run is made (as
+    sklearn does for an ndarray init); otherwise ``n_init`` k-means++ seedings drawn from ONE
+    ``RandomState(0)`` stream as sklearn draws them, and the run with the lowest inertia wins (a later
+    run replaces the best only if its inertia is lower and its clustering differs, _kmeans.py:1516-1530)."""
     global last_kmeans_report
     logger.debug("Clustering frames with kmeans...")
     Y = _to_device(feature_matrix)
@@ -214,10 +222,16 @@ def kmeans_clustering(feature_matrix, num_clusters: int, n_init: int,
         num_clusters = init.shape[0]
         runs.append(kmeans_lloyd(Y, init))
     else:
-        for s in range(max(1, int(n_init))):
-            runs.append(kmeans_lloyd(Y, _kmeanspp_init(Y, num_clusters, seed=s)))
+        rs = np.random.RandomState(0)
+        x_mean = Y.to(torch.float64).mean(dim=0)
+        Yc = (Y - x_mean.to(Y.dtype)).contiguous()
+        for _ in range(max(1, int(n_init))):
+            runs.append(kmeans_lloyd(Y, _kmeanspp_sklearn(Yc, num_clusters, rs) + x_mean))
     logger.debug("Number of clusters: {}".format(num_clusters))
-    best = min(runs, key=lambda r: r["inertia"])
+    best = runs[0]
+    for r in runs[1:]:
+        if r["inertia"] < best["inertia"]:
+            best = r
     last_kmeans_report = {"n_iter": best["n_iter"], "strict": best["strict"], "ties": best["ties"],
                           "inertia": best["inertia"], "n_runs": len(runs)}
     if best["ties"]:
@@ -234,49 +248,92 @@ def cluster_data(features, settings: Dict, initial_centroids=None) -> Tuple[np.n
     if settings["algorithm"] == "kmeans":
         return kmeans_clustering(features, settings["num_clusters"], settings["n_init"], initial_centroids)
     if settings["algorithm"] in ("hdbscan", "hierarchical"):
-        raise NotImplementedError(
-            f"clustering algorithm {settings['algorithm']} is outside the B200 hot path "
-            "(SURVEY.md section 2); use algorithm: kmeans or the reference package")
+        _outside_hot_path(settings["algorithm"])
     raise Exception(f"clustering algorithm {settings['algorithm']} not implemented")
 
 
 def cluster_scores(features, labels, centers=None) -> Dict[str, float]:
     """Calinski-Harabasz and Davies-Bouldin scores (sklearn definitions, used at reference
-    statistics.py:73-74) from per-cluster sums computed on the device in FP64."""
-    Y = _to_device(features).to(torch.float64)
+    statistics.py:73-74): counts and means of the members from FP64 reductions, the per-cluster
+    dispersion sums from one pass of ``dcg_cluster_dispersion``."""
+    Y = _to_device(features)
     lab = torch.as_tensor(np.asarray(labels), device=Y.device).long()
     n, d = Y.shape
     ids, inv = torch.unique(lab, return_inverse=True)
     k = ids.numel()
+    Yd = Y.to(torch.float64)
     cnt = torch.zeros(k, dtype=torch.float64, device=Y.device).index_add_(0, inv, torch.ones(n, dtype=torch.float64, device=Y.device))
-    cent = torch.zeros((k, d), dtype=torch.float64, device=Y.device).index_add_(0, inv, Y) / cnt[:, None]
-    diff = Y - cent[inv]
-    sq = (diff ** 2).sum(dim=1)
-    intra_disp = float(sq.sum().item())
-    mean = Y.mean(dim=0)
+    cent = torch.zeros((k, d), dtype=torch.float64, device=Y.device).index_add_(0, inv, Yd) / cnt[:, None]
+    ssq, sdist = ops.cluster_dispersion(Y, inv.to(torch.int32), cent)
+    intra_disp = float(ssq.sum().item())
+    mean = Yd.mean(dim=0)
     extra_disp = float((cnt * ((cent - mean) ** 2).sum(dim=1)).sum().item())
     ch = 1.0 if intra_disp == 0.0 else extra_disp * (n - k) / (intra_disp * (k - 1.0))
-    s = torch.zeros(k, dtype=torch.float64, device=Y.device).index_add_(0, inv, sq.sqrt()) / cnt
+    sk = sdist / cnt
     D = torch.cdist(cent, cent)
-    if torch.allclose(s, torch.zeros_like(s)) or torch.allclose(D, torch.zeros_like(D)):
+    if torch.allclose(sk, torch.zeros_like(sk)) or torch.allclose(D, torch.zeros_like(D)):
         db = 0.0
     else:
         D = D.masked_fill(D == 0, float("inf"))
-        db = float(((s[:, None] + s[None, :]) / D).max(dim=1).values.mean().item())
+        db = float(((sk[:, None] + sk[None, :]) / D).max(dim=1).values.mean().item())
     return {"calinski_harabasz": float(ch), "davies_bouldin": db}
 
 
+def silhouette(features, labels, sample_size: Optional[int] = None, seed: int = 0, chunk: int = 2048) -> float:
+    """Mean silhouette coefficient (sklearn ``silhouette_score``, Euclidean; reference statistics.py:75)
+    on the device in FP64: for every frame i, a_i = mean distance to the other members of its cluster,
+    b_i = the smallest mean distance to the members of another cluster, s_i = (b_i - a_i) / max(a_i, b_i)
+    (0 for singleton clusters).  O(N^2 d): ``sample_size`` evaluates it on a uniform random subsample
+    of that many frames against each other -- sklearn's own ``sample_size`` estimator."""
+    Y = _to_device(features).to(torch.float64)
+    lab = torch.as_tensor(np.asarray(labels), device=Y.device).long()
+    n = Y.shape[0]
+    if sample_size is not None and sample_size < n:
+        idx = torch.from_numpy(np.random.RandomState(seed).permutation(n)[:sample_size]).to(Y.device)
+        Y, lab = Y[idx], lab[idx]
+        n = sample_size
+    ids, inv = torch.unique(lab, return_inverse=True)
+    k = ids.numel()
+    if not 2 <= k <= n - 1:
+        raise ValueError("Number of labels is %d. Valid values are 2 to n_samples - 1 (inclusive)" % k)
+    onehot = torch.zeros((n, k), dtype=torch.float64, device=Y.device)
+    onehot[torch.arange(n, device=Y.device), inv] = 1.0
+    cnt = onehot.sum(dim=0)
+    total = torch.zeros((), dtype=torch.float64, device=Y.device)
+    for s0 in range(0, n, chunk):
+        e0 = min(n, s0 + chunk)
+        Dc = torch.cdist(Y[s0:e0], Y) @ onehot                          # (chunk, k): summed distances to every cluster
+        own = inv[s0:e0]
+        rows = torch.arange(e0 - s0, device=Y.device)
+        n_own = cnt[own]
+        a = Dc[rows, own] / (n_own - 1).clamp(min=1.0)
+        Dm = Dc / cnt[None, :]
+        Dm[rows, own] = float("inf")
+        b = Dm.min(dim=1).values
+        sil = (b - a) / torch.maximum(a, b)
+        sil = torch.where(n_own > 1, sil, torch.zeros_like(sil))
+        total += torch.nan_to_num(sil).sum()
+    return float((total / n).item())
+
+
 def optimize_clustering(features, settings: Dict):
-    """Reference statistics.py:17-110 for KMeans.  Scans ``search_interval`` and picks the best k
-    by the min-max normalised (CH - DB [+ silhouette]) score.  The O(N^2) silhouette term is
-    included (scikit-learn, on the host) only when N <= settings['silhouette_max_samples']
-    (default 20000); beyond that it is dropped and the combination is (CH - DB) / 2."""
+    """Reference statistics.py:17-110 for KMeans: every k of ``search_interval`` is clustered and scored
+    with Calinski-Harabasz, Davies-Bouldin and the mean silhouette; each score is min-max normalised over
+    the interval and the best k maximises (CH - DB + silhouette) / 3.  Like the reference it mutates
+    ``settings['num_clusters']`` and ignores ``opt_num_clusters``.  The silhouette is exact up to
+    ``settings['silhouette_max_samples']`` frames (default 50000, O(N^2) on the device); beyond that it is
+    sklearn's ``sample_size`` estimator on that many frames (seed 0) and a warning says so."""
     if settings.get("algorithm", "kmeans") != "kmeans":
-        raise NotImplementedError("only kmeans is accelerated; see cluster_data")
+        _outside_hot_path(settings.get("algorithm"))
     lo, hi = settings.get("search_interval", [2, 15])
     ks = list(range(lo, hi + 1))
     feats = np.asarray(features)
-    use_sil = feats.shape[0] <= int(settings.get("silhouette_max_samples", 20000))
+    max_sil = int(settings.get("silhouette_max_samples", 50000))
+    sample = None
+    if feats.shape[0] > max_sil:
+        sample = max_sil
+        logger.warning(f"Silhouette score estimated on a random subsample of {max_sil} of {feats.shape[0]} frames "
+                       "(scikit-learn's sample_size estimator); the reference evaluates all pairs")
     ch, db, sil, results = [], [], [], []
     for k in ks:
         settings["num_clusters"] = k
@@ -284,21 +341,37 @@ def optimize_clustering(features, settings: Dict):
         sc = cluster_scores(feats, labels)
         ch.append(sc["calinski_harabasz"])
         db.append(sc["davies_bouldin"])
-        if use_sil:
-            from sklearn.metrics import silhouette_score
-            sil.append(silhouette_score(feats, labels))
+        sil.append(silhouette(feats, labels, sample_size=sample))
+        logger.debug(f"Calinski-Harabasz score: {round(ch[-1], 3)}")
+        logger.debug(f"Davies-Bouldin score: {round(db[-1], 3)}")
+        logger.debug(f"Average silhouette score: {round(sil[-1], 3)}")
         results.append((labels, centroids))
 
     def norm(v):
         v = np.asarray(v, dtype=np.float64)
         return (v - v.min()) / (v.max() - v.min())
-    score = (norm(ch) - norm(db) + norm(sil)) / 3 if use_sil else (norm(ch) - norm(db)) / 2
+    score = (norm(ch) - norm(db) + norm(sil)) / 3
     best = int(np.argmax(score))
     logger.info(f"Best number of clusters: {ks[best]}")
     labels, centroids = results[best]
     if len(centroids) == 0:
         logger.warning("No clusters found using the provided settings. Try different settings or a different algorithm")
+    global last_optimize_report
+    last_optimize_report = {"k": ks, "calinski_harabasz": ch, "davies_bouldin": db, "silhouette": sil,
+                            "score": score.tolist(), "best_k": ks[best]}
     return labels, centroids
+
+
+last_optimize_report: Dict = {}
+
+
+def _outside_hot_path(algorithm):
+    """hdbscan / hierarchical clustering are not part of the B200 hot path: say so
+    the way the reference reports fatal configuration problems -- log an error and exit -- instead of a
+    traceback."""
+    logger.error(f"Clustering algorithm '{algorithm}' is outside the B200 hot path (only 'kmeans' is accelerated); "
+                 "set traj_cluster.algorithm: kmeans or use the reference package for it. Exiting...")
+    sys.exit(1)
 
 
 def find_centroids(data: pd.DataFrame, centroids: np.ndarray, clustering_features: List[str]) -> pd.DataFrame:

@@ -555,3 +555,22 @@ def fes_density(P: torch.Tensor, cols, bounds, num_bins: int, bandwidth: float, 
           _ptr(tmp), _stream(dev))
     _count(2 if dim == 1 else 3)
     return dens, frames, outside
+
+
+# ---- N1: clustering scores ------------------------------------------------------------------------
+def cluster_dispersion(Y: torch.Tensor, labels: torch.Tensor, means: torch.Tensor):
+    """Per-cluster ``sum ||y - m_c||^2`` and ``sum ||y - m_c||`` (FP64) in one pass over the frames:
+    what Calinski-Harabasz and Davies-Bouldin need besides the counts and the means."""
+    _need_cuda("Y", Y)
+    _need_cuda("labels", labels, torch.int32)
+    _need_cuda("means", means, torch.float64)
+    n, d, ld = _rows("Y", Y)
+    k = means.shape[0]
+    if means.dim() != 2 or means.shape[1] != d or labels.numel() != n:
+        raise ValueError("means must be (k, d) and labels must have one entry per frame")
+    ssq = torch.empty(k, dtype=torch.float64, device=Y.device)
+    sdist = torch.empty(k, dtype=torch.float64, device=Y.device)
+    _call(Y.device, "dcg_cluster_dispersion", Y.data_ptr(), n, d, ld, _dtype_bytes(Y), labels.contiguous().data_ptr(),
+          means.contiguous().data_ptr(), k, ssq.data_ptr(), sdist.data_ptr(), _stream(Y.device))
+    _count(1)
+    return ssq, sdist

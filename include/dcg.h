@@ -231,6 +231,14 @@ int dcg_ticaloss_f64(const double* sums, int d, double reg, int n_eig, double* r
 int dcg_gen_eig_small_f64(const double* H, const double* G, int b, int batch,
                           double* theta, double* S, double* status, void* stream);
 
+/* ---- N1: dispersion sums for the clustering scores -------------------------------------------------
+ * For sklearn's calinski_harabasz_score / davies_bouldin_score as called at
+ * modules/statistics/statistics.py:73-74: per cluster c (labels int32 in [0, k), means k x d FP64 =
+ * the means of the members), ssq[c] = sum ||y_t - m_c||^2 and sdist[c] = sum ||y_t - m_c|| over the
+ * members, FP64, in one pass over Y (n x d, float32 or float64).  Outputs are overwritten.           */
+int dcg_cluster_dispersion(const void* Y, int64_t n, int d, int64_t ld, int dtype_bytes, const int* labels,
+                           const double* means, int k, double* ssq, double* sdist, void* stream);
+
 /* ---- N4: free-energy surface by binned kernel density estimation ---------------------------------
  * Replaces mlcolvar.utils.fes.compute_fes(backend="KDEpy") as called at modules/figures/figures.py:95
  * (from tools/train_colvars/train_colvars_workflow.py:146-182).  KDEpy's FFTKDE = linear binning onto

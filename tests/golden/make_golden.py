@@ -115,12 +115,24 @@ def main():
         km[f"{name}_init"] = init
         km[f"{name}_labels"] = labels.astype(np.int32)
         km[f"{name}_centers"] = centers
+    # ---- the reference's DEFAULT search path: optimize_clustering (k-means++ with random_state=0, three
+    # scores per k) and kmeans_clustering without initial centroids, run by the imported reference module
+    from deep_cartograph.modules.statistics.statistics import kmeans_clustering, optimize_clustering
+    cent = rng.uniform(-0.8, 0.8, size=(5, 3))
+    Xo = np.ascontiguousarray(np.round(cent[rng.integers(0, 5, size=6000)] + 0.09 * rng.standard_normal((6000, 3)), 4))
+    lab_o, cen_o = optimize_clustering(Xo.copy(), {"algorithm": "kmeans", "search_interval": [2, 8], "n_init": 3})
+    km["opt_X"], km["opt_labels"], km["opt_centers"] = Xo, lab_o.astype(np.int32), cen_o
+    lab_p, cen_p = kmeans_clustering(Xo.copy(), 6, 4)
+    km["pp_labels"], km["pp_centers"] = lab_p.astype(np.int32), cen_p
+    from sklearn.metrics import calinski_harabasz_score, davies_bouldin_score, silhouette_score
+    km["pp_scores"] = np.array([calinski_harabasz_score(Xo, lab_p), davies_bouldin_score(Xo, lab_p),
+                                silhouette_score(Xo, lab_p)])
     np.savez_compressed(os.path.join(HERE, "kmeans_ref.npz"), **km)
 
     # ---- FES: the reference's own legacy output (mlcolvar compute_fes through KDEpy; bandwidth 0.025,
     # 200 bins, 300 K: data/calpha_transitions/input/distances_config.yml:93-95) and the projected
     # trajectory it was computed from
-    import pandas as pd
+
     base = os.path.join(REF, "deep_cartograph", "data", "calpha_transitions", "reference", "1rcs_B-3ssx_R-3",
                         "train_colvars", "pca")
     d = pd.read_csv(os.path.join(base, "projected_trajectory.csv"))

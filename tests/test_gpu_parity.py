@@ -1191,3 +1191,86 @@ def test_train_colvars_writes_fes_files(dev, c1, tmp_path):
         fes = np.load(os.path.join(base, sub, "fes.npy"))
         assert fes.shape == shape and np.isfinite(fes).all() and fes.min() == 0.0
         assert os.path.exists(os.path.join(base, sub, "fes_grid.npy"))
+
+
+# ------------------------------------------------------------------------------------------------
+# N3 PLUMED export of linear CVs
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cv", ["pca", "tica", "htica"])
+def test_plumed_combine_lines_reproduce_the_projected_csv(dev, c1, tmp_path, cv):
+    """The reference's end-to-end check (tests/test_deep_cartograph.py:209-258: PLUMED's projection of
+    the linear CVs vs the CSV, |diff| < 1e-2) with the COMBINE arithmetic evaluated in float64: the
+    parameters get_cv_parameters() hands to the PLUMED assembler (assembler.py:333-379) reproduce the
+    CSV train_colvars wrote -- and the reference's golden CSV."""
+    from deep_cartograph_b200.modules.cv_learning.cv_calculator import CVCalculator
+    from deep_cartograph_b200.modules.plumed.input import assembler
+    from deep_cartograph_b200.tools import train_colvars
+    feats = [l.strip() for l in open(os.path.join(GOLDEN, "peptide_c1_features.txt")) if l.strip()]
+    cfg = _config("auto")
+    cfg["cvs"] = [cv]
+    out = train_colvars(configuration=cfg, train_colvars_paths=[os.path.join(GOLDEN, "peptide_c1.dat")],
+                        trajectory_names=["CA_example"], features_list=feats, output_folder=str(tmp_path / "tc"))
+    calc = CVCalculator.load(out[cv]["model_path"], str(tmp_path / "loaded"))
+    params = calc.get_cv_parameters()
+    # a loaded model has no training projection: cv_stats come back from the stored CV normalisation
+    assert params["features_norm_mean"].dtype == np.float32 and params["weights"].shape == (len(feats), 2)
+    params["features_norm_mode"] = "mean_std"
+    params["cv_stats"] = {"min": calc.cv_norm_mean - calc.cv_norm_range, "max": calc.cv_norm_mean + calc.cv_norm_range}
+    text, labels = assembler.add_linear_cv(params, feats)
+    assert text.count("COMBINE") == len(feats) + 4 and all(" PERIODIC=NO" in l for l in text.splitlines() if "COMBINE" in l)
+    table = {name: c1["X"][:, i] for i, name in enumerate(feats)}
+    vals = assembler.evaluate_combine(text, table, labels)
+    plumed_proj = np.stack([vals[l] for l in labels], axis=1)
+    csv = pd.read_csv(out[cv]["traj_paths"][0]).to_numpy()
+    assert np.abs(plumed_proj - csv).max() < 1.5e-4                      # 4-decimal print + float32 projection
+    assert np.abs(plumed_proj - c1[f"{cv}_csv"]).max() < 1e-2            # the reference's threshold
+
+
+# ------------------------------------------------------------------------------------------------
+# K2 / N1: the reference's default clustering path (k-means++ seeding, scores, choice of k)
+# ------------------------------------------------------------------------------------------------
+def test_kmeans_plus_plus_and_scores_match_the_reference(dev, kmeans_ref):
+    """kmeans_clustering WITHOUT initial centroids == the reference's KMeans(random_state=0,
+    init='k-means++', n_init) (tests/golden/kmeans_ref.npz: produced by the reference's imported
+    statistics.kmeans_clustering), and the three model-selection scores == scikit-learn's on its labels."""
+    from deep_cartograph_b200.modules.statistics import statistics
+    X = kmeans_ref["opt_X"]
+    labels, centers = statistics.kmeans_clustering(X.copy(), 6, 4)
+    np.testing.assert_array_equal(labels, kmeans_ref["pp_labels"])
+    np.testing.assert_allclose(centers, kmeans_ref["pp_centers"], rtol=1e-10, atol=1e-12)
+    sc = statistics.cluster_scores(X, labels)
+    ch, db, sil = kmeans_ref["pp_scores"]
+    assert abs(sc["calinski_harabasz"] - ch) <= 1e-9 * ch
+    assert abs(sc["davies_bouldin"] - db) <= 1e-9 * db
+    assert abs(statistics.silhouette(X, labels) - sil) <= 1e-9
+    # sklearn's sample_size estimator: a subsample scored against itself
+    from sklearn.metrics import silhouette_score
+    est = statistics.silhouette(X, labels, sample_size=2000, seed=0)
+    idx = np.random.RandomState(0).permutation(X.shape[0])[:2000]
+    assert abs(est - silhouette_score(X[idx], labels[idx])) <= 1e-9
+
+
+def test_optimize_clustering_matches_the_reference(dev, kmeans_ref):
+    """The default traj_cluster path for kmeans (reference statistics.py:54-100): same k, same labels,
+    same centres as the reference's own optimize_clustering on the same frames."""
+    from deep_cartograph_b200.modules.statistics import statistics
+    settings = {"algorithm": "kmeans", "search_interval": [2, 8], "n_init": 3}
+    labels, centers = statistics.optimize_clustering(kmeans_ref["opt_X"].copy(), settings)
+    assert centers.shape == kmeans_ref["opt_centers"].shape, statistics.last_optimize_report
+    np.testing.assert_array_equal(labels, kmeans_ref["opt_labels"])
+    np.testing.assert_allclose(centers, kmeans_ref["opt_centers"], rtol=1e-10, atol=1e-12)
+    assert settings["num_clusters"] == 8                   # mutated like the reference (statistics.py:67)
+
+
+def test_cluster_dispersion_kernel(dev):
+    from deep_cartograph_b200 import ops
+    rng = np.random.default_rng(4)
+    for dt in (np.float32, np.float64):
+        Y = rng.normal(size=(50_001, 7)).astype(dt)
+        lab = rng.integers(0, 13, size=50_001).astype(np.int32)
+        lab[:4000] = 5                                      # a run of equal labels (warp-uniform path)
+        means = np.stack([Y[lab == c].astype(np.float64).mean(0) for c in range(13)])
+        ssq, sdist = ops.cluster_dispersion(_cuda(Y, dev), _cuda(lab, dev), _cuda(means, dev))
+        q = ((Y.astype(np.float64) - means[lab]) ** 2).sum(1)
+        np.testing.assert_allclose(ssq.cpu().numpy(), np.bincount(lab, weights=q, minlength=13), rtol=1e-12)
+        np.testing.assert_allclose(sdist.cpu().numpy(), np.bincount(lab, weights=np.sqrt(q), minlength=13), rtol=1e-12)

@@ -429,12 +429,18 @@ def test_lloyd_driver_control_flow_with_emulated_kernel(monkeypatch, kmeans_ref)
     np.testing.assert_allclose(res["centers"].numpy(), ref["centers"], rtol=1e-12)
 
 
-def test_cluster_data_rejects_out_of_scope_algorithms():
+def test_cluster_data_rejects_out_of_scope_algorithms(caplog):
+    """hdbscan / hierarchical are outside the hot path: reported the reference's way (error logged,
+    sys.exit(1)), not as a traceback -- this is what traj_cluster(configuration={}) runs into, whose
+    schema default is hierarchical (reference yaml_schemas/traj_cluster.py:25)."""
     from deep_cartograph_b200.modules.statistics import statistics
-    with pytest.raises(NotImplementedError):
-        statistics.cluster_data(np.zeros((4, 2)), {"algorithm": "hdbscan"})
-    with pytest.raises(NotImplementedError):
-        statistics.cluster_data(np.zeros((4, 2)), {"algorithm": "hierarchical"})
+    for algo in ("hdbscan", "hierarchical"):
+        with pytest.raises(SystemExit) as ex:
+            statistics.cluster_data(np.zeros((4, 2)), {"algorithm": algo})
+        assert ex.value.code == 1
+    with pytest.raises(SystemExit):
+        statistics.optimize_clustering(np.zeros((4, 2)), {"algorithm": "hierarchical"})
+    assert "outside the B200 hot path" in caplog.text
 
 
 def test_deeptica_covariance_backward_formula_cpu(monkeypatch):
