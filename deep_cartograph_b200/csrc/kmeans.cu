@@ -418,14 +418,12 @@ extern "C" int dcg_kmeans_step(const void* Y, int64_t n, int d, int64_t ld, int 
       DCG_CUDA_TRY(cudaMemsetAsync(counts, 0, (size_t)k * sizeof(double), st));
     }
   }
-  // many centres: the scan runs on the tensor cores (kmeans_tc.cu) when the data bound is known
-  // (DCG_KMEANS_TC: 0 = CUDA cores only, 1 = tcgen05 / TMEM variant, otherwise the register-resident scan)
+  // many centres: the scan runs on the tensor cores (kmeans_mma.cu) when the data bound is known
+  // (DCG_KMEANS_TC=0 forces the CUDA-core kernel)
   {
     const char* sel = getenv("DCG_KMEANS_TC");
     int rc = DCG_E_MODE;
-    if (sel && sel[0] == '1')
-      rc = kmeans_tc_launch(Y, dtype_bytes, n, d, ld, centers, k, labels, sums, counts, stats, gap, update_sums, y_absmax, st);
-    else if (!(sel && sel[0] == '0'))
+    if (!(sel && sel[0] == '0'))
       rc = kmeans_mma_launch(Y, dtype_bytes, n, d, ld, centers, k, labels, sums, counts, stats, gap, update_sums, y_absmax, st);
     if (rc != DCG_E_MODE) return rc;
   }

@@ -62,14 +62,10 @@ __device__ __forceinline__ void km_add_fixed(double* slot, double v) {
 }
 
 
-// Tensor-core E-steps for many centres: register-resident scan on mma.sync (kmeans_mma.cu, the
-// default) and the tcgen05 / TMEM variant (kmeans_tc.cu, DCG_KMEANS_TC=1).  Both return DCG_E_MODE
-// when the shape is outside their range (the caller then takes the CUDA-core kernel).
+// Tensor-core E-step for many centres: register-resident scan on mma.sync (kmeans_mma.cu).  Returns
+// DCG_E_MODE when the shape is outside its range (the caller then takes the CUDA-core kernel).
 int kmeans_mma_launch(const void* Y, int dtype_bytes, int64_t n, int d, int64_t ld, const double* centers, int k,
                       int32_t* labels, double* sums, double* counts, double* stats, void* gap,
                       int update_sums, const double* y_absmax, cudaStream_t st);
-int kmeans_tc_launch(const void* Y, int dtype_bytes, int64_t n, int d, int64_t ld, const double* centers, int k,
-                     int32_t* labels, double* sums, double* counts, double* stats, void* gap,
-                     int update_sums, const double* y_absmax, cudaStream_t st);
 
 }  // namespace dcg

@@ -1,12 +1,24 @@
 // K1 with many centres, register-resident scan: the scores of 32 frames against 8 centres are
 // warp-level tensor-core MMAs (mma.sync.m16n8k16, FP16 hi/lo split, K = d + 1 <= 16) whose
 // accumulators ARE the scores, already in registers, so the arg-min scan costs 5 ALU operations
-// per score and nothing else.  Same arithmetic, scaling, screening bound and FP64 refine as the
-// tcgen05 variant (kmeans_tc.cu, see its header for the error analysis); what differs is where
-// the scores land.  With tcgen05 they land in TMEM and must come back through its 64 B/clk read
-// port: 512 KB per 128-frame tile at k = 1000 = 8.2 k cycles, measured 7.4 ms per 12.5 M frames
-// with the tile-serial protocol; here the bound is the scan itself (5 k / 128 cycles per frame
-// and SM) next to 3 HMMAs per 128 scores.
+// per score and nothing else.  (A tcgen05 / TMEM variant -- M = 128 x N = 256 x K = 16 kind::f16 MMAs,
+// scan warps on tcgen05.ld -- was measured in round 1 and dropped: every score has to come back through
+// the 64 B/clk TMEM read port, 512 KB per 128-frame tile at k = 1000 = 8.2 k cycles, 7.4 ms per 12.5 M
+// frames against 4.4 ms here, where the bound is the scan itself, 5 k / 128 cycles per frame and SM,
+// next to 3 HMMAs per 128 scores.)
+//
+// Precision.  score[t, j] = ||c_j||^2 - 2 y_t . c_j is the GEMM [y_t, 1] x [-2 c_j ; ||c_j||^2] with
+// K = d + 1 <= 16.  Both operands are split into FP16 hi + lo pieces (11 bits each, three MMAs:
+// hi*hi + hi*lo + lo*hi) after scaling the data and the centres by a power of two so that everything
+// lies in [-1, 1]; the result carries FP32-like error.  As in the CUDA-core kernel this is only a
+// SCREEN: a frame whose two best screened scores are closer than a rigorous bound on that error is
+// re-evaluated over all centres in FP64 from the original data by its whole warp, so the label is
+// always the FP64 arg-min with the lowest-index tie-break.  The bound, in scaled units, with
+// B = max_j ||c_j||^2 + 2 |y| max_j |c_j| >= |score|:  dropped lo*lo and split residuals
+// 3 * 2^-24 * 2|y||c|, float32 rounding of centres / float64 frames 2 * 2^-24 * 2|y||c|, ||c||^2
+// pieces 2 * 2^-24 * ||c||^2, FP16 subnormal floor 3 * 2^-25 * d, accumulator adds plus the in-MMA
+// product sums 6 * 2^-23 * B: <= 9.5 * 2^-23 * B + 0.75 * 2^-23 * d per score, twice that for a
+// difference of two, times 1.5:  eps = 3.4e-6 * B + 3e-7 * d.
 //
 // Per warp: 32 frames (two m16 tiles).  Lane (g = lane / 4, t = lane % 4) holds, of rows g, g + 8,
 // g + 16, g + 24, the coordinates q in {2t, 2t+1, 2t+8, 2t+9} -- raw (for the M-step sums) and as

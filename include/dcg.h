@@ -163,7 +163,7 @@ int dcg_project_blocks_f32(const float* X, int64_t n, int f, int64_t ld,
  * With y_absmax, d <= 15 and 256 <= k <= 2048 (or k >= 64 and d >= 8) the scores are screened
  * on the tensor cores (FP16-split GEMM, operands scaled into [-1, 1] by the bound; kmeans_mma.cu)
  * with the same rigorous near-tie test and FP64 refine: the labels are unchanged, k = 1000 is
- * twice as fast.  Env DCG_KMEANS_TC=0 forces the CUDA-core kernel, =1 the tcgen05 / TMEM variant. */
+ * twice as fast.  Env DCG_KMEANS_TC=0 forces the CUDA-core kernel.                             */
 size_t dcg_kmeans_workspace_bytes(int64_t n, int d, int k, int dtype_bytes);
 int dcg_kmeans_step(const void* Y, int64_t n, int d, int64_t ld, int dtype_bytes,
                     const double* centers, int k, int32_t* labels,
