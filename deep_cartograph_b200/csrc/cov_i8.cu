@@ -155,7 +155,10 @@ i8_quantize_kernel(const float* __restrict__ X, int64_t row0, int64_t pairs, int
   uint32_t (*tile)[kQF][kQRow] = reinterpret_cast<uint32_t (*)[kQF][kQRow]>(qsmem);   // [3 or 6 planes][feature][word]
   __shared__ unsigned long long ssum[2][kQF];
   const int tid = threadIdx.x;
-  const int fe4 = tid & 15, frq = tid >> 4;            // 4 features x 4 frames per thread and pass
+  // 4 features x 4 frames per thread and pass.  A warp covers 8 feature quads x 4 frame quads so that its
+  // transposed shared-memory stores (word index 33 * feature + frame quad) hit 32 different banks; its
+  // global loads are 128-byte row segments.
+  const int fe4 = ((tid >> 5) & 1) * 8 + (tid & 7), frq = (tid >> 6) * 4 + ((tid >> 3) & 3);
   const int f0 = blockIdx.x * kQF;
   const int fc = f0 + 4 * fe4;
   float c[4], m[4];
@@ -390,6 +393,7 @@ cov_i8_kernel(const __grid_constant__ CUtensorMap map_a,      // planes [set][di
   const uint32_t smem_base = (smem_u32(smem_raw8) + 1023u) & ~1023u;
   __shared__ uint64_t full_bar[8], empty_bar[8], acc_full, acc_empty;
   __shared__ uint32_t tmem_base_s;
+  __shared__ double epi_smem[4 * 32 * 9];          // per epilogue warp: 32 rows x 8 columns (+1 padding)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank8();
@@ -485,11 +489,15 @@ cov_i8_kernel(const __grid_constant__ CUtensorMap map_a,      // planes [set][di
       const uint32_t lane_base = (uint32_t)(q * 32) << 16;
       mbar_wait(&acc_full, gi & 1);
       tc_fence_after();
-      const int gi_row = td.i0 + (int)rank * kHalfM + 32 * q + lane;
+      // Row `32 q + lane` of this CTA's half of the tile sits in this lane.  The FP64 adds go out 8 columns
+      // of 4 rows per instruction (64 contiguous bytes per row) through a small shared-memory transpose:
+      // one row per lane would touch 32 different lines per instruction (measured: 20 us per work item).
+      const int row0 = td.i0 + (int)rank * kHalfM + 32 * q;
+      const int gi_row = row0 + lane;
       const bool row_ok = gi_row < td.i_hi;
       const double si = row_ok ? p.scale[gi_row] : 0.0;
-      double* out = (td.kind == 0 ? p.S0 : p.St) + (size_t)(row_ok ? gi_row : 0) * p.f;
-      const int j_min = gi_row;                                // both Grams are symmetric: upper triangle only
+      double* sE = epi_smem + (warp - 2) * (32 * 9);
+      double* outm = td.kind == 0 ? p.S0 : p.St;
       for (int c0 = 0; c0 < N && !(p.dbg & 4); c0 += 16) {
         uint32_t va[16], vb[16], vc[16], vd[16];
         tmem_ld_x16(tmem + lane_base + c0, va);
@@ -497,18 +505,27 @@ cov_i8_kernel(const __grid_constant__ CUtensorMap map_a,      // planes [set][di
         tmem_ld_x16(tmem + 2 * N + lane_base + c0, vc);
         tmem_ld_x16(tmem + 3 * N + lane_base + c0, vd);
         tmem_ld_wait();
-        if (row_ok) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int gj = td.j0 + c0 + j;
-            if (gj < td.j_hi && gj >= j_min) {
-              // sum of the digit products down to weight 2^8 (only d0 d0 is left out): an integer below
-              // 2^63 whose double is exact to 2^-53 relative
-              const double v = (double)(int)va[j] * 4294967296.0 + (double)(int)vb[j] * 16777216.0 +
-                               (double)(int)vc[j] * 65536.0 + (double)(int)vd[j] * 256.0;
-              atomicAdd(out + gj, v * si * p.scale[gj]);
-            }
+        for (int half = 0; half < 2; ++half) {
+          const int cb = td.j0 + c0 + 8 * half;                   // first column of this group of 8
+          if (cb >= td.j_hi || cb + 7 < row0) continue;            // beyond the edge, or wholly below the diagonal (warp-uniform)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int jj = 8 * half + j, gj = cb + j;
+            // sum of the digit products down to weight 2^8 (only d0 d0 is left out): an integer below
+            // 2^63 whose double is exact to 2^-53 relative
+            const double v = (double)(int)va[jj] * 4294967296.0 + (double)(int)vb[jj] * 16777216.0 +
+                             (double)(int)vc[jj] * 65536.0 + (double)(int)vd[jj] * 256.0;
+            sE[lane * 9 + j] = gj < td.j_hi ? v * si * p.scale[gj] : 0.0;
           }
+          __syncwarp();
+          const int col = lane & 7, gj = cb + col;
+#pragma unroll
+          for (int rr = 0; rr < 8; ++rr) {
+            const int row = 4 * rr + (lane >> 3), gi = row0 + row;
+            if (gi < td.i_hi && gj < td.j_hi && gj >= gi) atomicAdd(outm + (size_t)gi * p.f + gj, sE[row * 9 + col]);
+          }
+          __syncwarp();
         }
       }
       tc_fence_before();
