@@ -72,23 +72,53 @@ __host__ __device__ constexpr int stage_bytes(int N) { return 3 * kPlaneA + 3 * 
 inline int num_stages(int N) { return std::min(8, (int)((227 * 1024 - 2048) / stage_bytes(N))); }
 
 struct Tile8 {
-  int i0, j0;          // first feature of the tile rows / columns
-  int i_hi, j_hi;      // one past the last valid feature (block / matrix edge)
-  int kind;            // 0 = S0 = Z^T Z, 1 = G = U^T U; only entries j >= i are written
+  int ia0, ia1;        // first feature of the 128 rows staged by CTA 0 / CTA 1 of the pair (-1: none)
+  int j0;              // first feature of the N columns
+  int hi;              // one past the last valid feature (block / matrix edge), rows and columns
+  int kind;            // 0 = S0 = Z^T Z, 1 = G = U^T U; only the upper triangle (j >= i) is written
+  int tr0, tr1;        // the half computes a block BELOW the diagonal and writes its transpose
 };
 
+// Work tiles of one symmetric Gram per diagonal region (the whole matrix, or each hTICA block).
+// N == 128: the region is a grid of 128 x 128 blocks of which the upper triangle incl. the diagonal is
+// needed; a tile pairs two blocks that share their COLUMN block (the B operand of the pair MMA) -- a
+// block (r, c) may also be computed as (c, r) and written transposed, so the odd block left over in
+// every even column c = 4m (its diagonal block) is paired with the one of column 4m + 2, block (4m, 4m+2),
+// computed as (4m+2, 4m): nb (nb + 1) / 2 blocks in ceil(that / 2) tiles (18 instead of 20 at nb = 8, 5
+// instead of 6 at nb = 4).  Other N (narrow matrices): 256-row x N tiles that touch the upper triangle.
 __host__ __device__ inline int enum_tiles8(int f, int block, int N, bool want_s0, bool want_st, Tile8* out) {
   int n = 0;
   const int w = block > 0 ? block : f;
   for (int b0 = 0; b0 < f; b0 += w) {
     const int b1 = b0 + w < f ? b0 + w : f;
-    for (int i0 = b0; i0 < b1; i0 += kTileM)
-      for (int j0 = b0; j0 < b1; j0 += N)
-        for (int kind = 0; kind < 2; ++kind) {
-          if (!(kind == 0 ? want_s0 : want_st) || j0 + N <= i0) continue;
-          if (out) out[n] = Tile8{i0, j0, i0 + kTileM < b1 ? i0 + kTileM : b1, j0 + N < b1 ? j0 + N : b1, kind};
+    for (int kind = 0; kind < 2; ++kind) {
+      if (!(kind == 0 ? want_s0 : want_st)) continue;
+      if (N != kHalfM) {
+        for (int i0 = b0; i0 < b1; i0 += kTileM)
+          for (int j0 = b0; j0 < b1; j0 += N) {
+            if (j0 + N <= i0) continue;
+            if (out) out[n] = Tile8{i0, i0 + kHalfM < b1 ? i0 + kHalfM : -1, j0, b1, kind, 0, 0};
+            ++n;
+          }
+        continue;
+      }
+      const int nb = (b1 - b0 + kHalfM - 1) / kHalfM;
+      for (int c = 0; c < nb; ++c) {
+        const int skip = (c & 1) ? -1 : ((c & 3) == 0 ? c : c - 2);      // the block left over in an even column
+        int first = -1;
+        for (int r = 0; r <= c; ++r) {
+          if (r == skip) continue;
+          if (first < 0) { first = r; continue; }
+          if (out) out[n] = Tile8{b0 + first * kHalfM, b0 + r * kHalfM, b0 + c * kHalfM, b1, kind, 0, 0};
+          ++n;
+          first = -1;
+        }
+        if ((c & 3) == 0) {            // diagonal block (c, c) + block (c + 2, c), written transposed as (c, c + 2)
+          if (out) out[n] = Tile8{b0 + c * kHalfM, c + 2 < nb ? b0 + (c + 2) * kHalfM : -1, b0 + c * kHalfM, b1, kind, 0, 1};
           ++n;
         }
+      }
+    }
   }
   return n;
 }
@@ -427,7 +457,9 @@ cov_i8_kernel(const __grid_constant__ CUtensorMap map_a,      // planes [set][di
       // ===================== TMA producer (one lane per CTA) ===========================================
       if (lane == 0) {
         const int set = td.kind;                                   // 0: Z planes (S0), 1: U planes (G)
-        const int ia = td.i0 + (int)rank * kHalfM, jb = td.j0 + (int)rank * (N / 2);
+        // a CTA without a row block stages rows beyond the tensor extent: zero-filled by the TMA unit
+        const int ia_t = rank ? td.ia1 : td.ia0;
+        const int ia = ia_t < 0 ? p.f : ia_t, jb = td.j0 + (int)rank * (N / 2);
         for (uint32_t s = 0; s < nS; ++s) {
           const uint32_t g = gs + s, slot = g % NS;
           mbar_wait(&empty_bar[slot], ((g / NS) & 1) ^ 1);
@@ -492,13 +524,15 @@ cov_i8_kernel(const __grid_constant__ CUtensorMap map_a,      // planes [set][di
       // Row `32 q + lane` of this CTA's half of the tile sits in this lane.  The FP64 adds go out 8 columns
       // of 4 rows per instruction (64 contiguous bytes per row) through a small shared-memory transpose:
       // one row per lane would touch 32 different lines per instruction (measured: 20 us per work item).
-      const int row0 = td.i0 + (int)rank * kHalfM + 32 * q;
+      const int ia_t = rank ? td.ia1 : td.ia0;
+      const bool transposed = (rank ? td.tr1 : td.tr0) != 0;
+      const int row0 = ia_t + 32 * q;
       const int gi_row = row0 + lane;
-      const bool row_ok = gi_row < td.i_hi;
+      const bool row_ok = ia_t >= 0 && gi_row < td.hi;
       const double si = row_ok ? p.scale[gi_row] : 0.0;
       double* sE = epi_smem + (warp - 2) * (32 * 9);
       double* outm = td.kind == 0 ? p.S0 : p.St;
-      for (int c0 = 0; c0 < N && !(p.dbg & 4); c0 += 16) {
+      for (int c0 = 0; c0 < N && !(p.dbg & 4) && ia_t >= 0; c0 += 16) {
         uint32_t va[16], vb[16], vc[16], vd[16];
         tmem_ld_x16(tmem + lane_base + c0, va);
         tmem_ld_x16(tmem + N + lane_base + c0, vb);
@@ -508,7 +542,9 @@ cov_i8_kernel(const __grid_constant__ CUtensorMap map_a,      // planes [set][di
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           const int cb = td.j0 + c0 + 8 * half;                   // first column of this group of 8
-          if (cb >= td.j_hi || cb + 7 < row0) continue;            // beyond the edge, or wholly below the diagonal (warp-uniform)
+          if (cb >= td.hi) continue;                               // beyond the edge (warp-uniform)
+          if (!transposed && cb + 7 < row0) continue;              // wholly below the diagonal (warp-uniform)
+          double v8[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int jj = 8 * half + j, gj = cb + j;
@@ -516,14 +552,24 @@ cov_i8_kernel(const __grid_constant__ CUtensorMap map_a,      // planes [set][di
             // 2^63 whose double is exact to 2^-53 relative
             const double v = (double)(int)va[jj] * 4294967296.0 + (double)(int)vb[jj] * 16777216.0 +
                              (double)(int)vc[jj] * 65536.0 + (double)(int)vd[jj] * 256.0;
-            sE[lane * 9 + j] = gj < td.j_hi ? v * si * p.scale[gj] : 0.0;
+            v8[j] = gj < td.hi ? v * si * p.scale[gj] : 0.0;
           }
+          if (transposed) {
+            // block below the diagonal: entry (gi, gj) goes to (gj, gi); for a fixed column the 32 lanes
+            // write 32 consecutive doubles -- coalesced straight from the registers
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (row_ok && cb + j < td.hi) atomicAdd(outm + (size_t)(cb + j) * p.f + gi_row, v8[j]);
+            continue;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) sE[lane * 9 + j] = v8[j];
           __syncwarp();
           const int col = lane & 7, gj = cb + col;
 #pragma unroll
           for (int rr = 0; rr < 8; ++rr) {
             const int row = 4 * rr + (lane >> 3), gi = row0 + row;
-            if (gi < td.i_hi && gj < td.j_hi && gj >= gi) atomicAdd(outm + (size_t)gi * p.f + gj, sE[row * 9 + col]);
+            if (gi < td.hi && gj < td.hi && gj >= gi) atomicAdd(outm + (size_t)gi * p.f + gj, sE[row * 9 + col]);
           }
           __syncwarp();
         }
