@@ -34,7 +34,7 @@ sys.path.insert(0, ROOT)
 # committed `ncu --set full` captures under profiles/ (dram__bytes_read.sum + dram__bytes_write.sum).  A shape
 # without a capture reports null.
 TRAFFIC = {("tc_3xf16", 1_000_000, 1000): 11.88e9, ("tc_3xtf32", 1_000_000, 1000): 9.95e9,
-           ("tc_i8x3", 1_000_000, 1000): 13.56e9}
+           ("tc_i8x3", 1_000_000, 1000): 4.866e9}
 
 F = 1000
 N_PER_GPU = 1_000_000
@@ -584,7 +584,11 @@ def main():
         issued_ops = 2.0 * (2 * n_up) * 256 * 128 * 8 * M          # 2 Grams, 8 digit products, MAC = 2 ops
         achieved = alg_flops / (k_ms * 1e-3) / 1e12
         peak = peaks["bf16_tflops_sustained"]
-        roofline = {"bound": "tensor", "kernel": "cov_i8_kernel (tcgen05.mma.cta_group::2.kind::i8, TMA-staged digit planes)",
+        fused = q_ms < 0.05                     # the fused kernel quantises inside the contraction launch
+        roofline = {"bound": "tensor",
+                    "kernel": ("cov_i8_fused_kernel (quantiser warps -> L2-resident digit-plane ring -> TMA -> "
+                               "tcgen05.mma.cta_group::2.kind::i8, one persistent launch)" if fused else
+                               "cov_i8_kernel (tcgen05.mma.cta_group::2.kind::i8, TMA-staged digit planes)"),
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "peak_source": f"{peaks['source']} dense bf16, sustained (MEASURED_PEAKS.json)",
                     "kernel_ms": k_ms, "share_of_step": k_ms / ms_per_step,
@@ -593,14 +597,15 @@ def main():
                     "issued_int8_tops": issued_ops / (k_ms * 1e-3) / 1e12,
                     "int8_peak_derived_tops": 2.0 * peaks["bf16_tflops"],
                     "frac_issued_of_int8_peak_derived": issued_ops / (k_ms * 1e-3) / 1e12 / (2.0 * peaks["bf16_tflops"]),
-                    "quantize_kernel": {"ms": q_ms, "alg_bytes": 10.0 * f * n, "gbs": 10.0 * f * n / (q_ms * 1e-3) / 1e9,
-                                        "frac_hbm": 10.0 * f * n / (q_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                                        "note": "4 bytes read + 6 bytes of digit planes written per value (HBM-bound)"},
                     "call_ms": cov_s * 1e3,
                     "traffic": TRAFFIC.get((engine, n, f)),
                     "traffic_note": "dram bytes read + written per launch of this kernel from the committed ncu --set full "
                                     "capture of this shape (profiles/); algorithmic bytes of the whole covariance pass = "
                                     "4*F*n = %.3g" % (4.0 * f * n)}
+        if not fused:
+            roofline["quantize_kernel"] = {"ms": q_ms, "alg_bytes": 10.0 * f * n, "gbs": 10.0 * f * n / (q_ms * 1e-3) / 1e9,
+                                           "frac_hbm": 10.0 * f * n / (q_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                           "note": "4 bytes read + 6 bytes of digit planes written per value (HBM-bound)"}
     else:
         f16_kind = engine == "tc_3xf16"
         tf32_peak = peaks["bf16_tflops_sustained"] if f16_kind else peaks["bf16_tflops_sustained"] / 2.0

@@ -48,6 +48,7 @@
 #include <cuda.h>
 #include <cstdio>
 #include <cstdlib>
+#include <vector>
 #include "dcg_common.cuh"
 #include "tc_common.cuh"
 
@@ -141,6 +142,7 @@ __global__ void i8_prep_kernel(int f, const float* __restrict__ mean, const floa
   // largest power of two with amax * 2^e <= kQMax (one ulp of slack for the float32 subtraction)
   int e = ilogbf((float)kQMax / (amax * 1.0000002f));
   e = e > 100 ? 100 : (e < -100 ? -100 : e);
+  if (c != 0.f && isfinite(c)) e = min(e, 120 - ilogbf(c));       // c 2^e stays finite (the fused kernel's single FMA)
   shift[j] = c;
   mul[j] = ldexpf(1.f, e);
   scale[j] = ldexp(1.0, -e) / (double)r;
@@ -587,6 +589,530 @@ cov_i8_kernel(const __grid_constant__ CUtensorMap map_a,      // planes [set][di
   if (warp == 1) tmem_dealloc2_8(tmem, 512);
 }
 
+// ---- fused quantise + contraction (the default whenever the 128-wide tile plan applies) -------------------
+// One persistent kernel; the digit planes never leave L2.  The frames are cut into windows of Wf frames;
+// the planes of R consecutive windows live in a ring in global memory that is small enough to stay in L2.
+// Every CTA carries, next to the TMA / MMA / epilogue warps of the kernel above, kQuantWarps warps that
+// quantise the windows one ring slot ahead of the consumers:
+//     quantiser warp:  wait until every cluster has consumed window w - R   (counter done[w % kCtr])
+//                      quantise its share of window w into slot w % R        (32 features x 32 frames per item)
+//     signalling warp: (one per CTA; the quantisers talk to it through shared memory and never wait for a
+//                      device-scope fence themselves)  when the CTA's quantisers are through window w:
+//                      fence, release: ready[w % kCtr] += 1
+//     TMA producer:    wait until every CTA has released window w (counter ready[w % kCtr]), then
+//                      stage its cluster's share of the window exactly as above
+//     MMA issuer:      when the last stage of window w has landed: done[w % kCtr] += 1
+// The counters are monotonic (target x (w / kCtr + 1)); kCtr >= R makes the modulo safe: a quantiser can only
+// reach window w + kCtr after every cluster has consumed window w + kCtr - R >= w.
+// Work is TILE-STATIONARY: cluster c owns unit c = (tile, frame split) for the whole launch and accumulates
+// it in TMEM across windows; the int32 accumulators are flushed to the FP64 result every 32768 frames.
+// n_tiles > clusters: several launches ("rounds"), each quantising only the features its tiles touch.
+// All CTAs of the grid must be co-resident (they wait on each other): the host launches no more clusters than
+// cudaOccupancyMaxActiveClusters reports.
+// Warp roles of the fused kernel, by warpgroup (setmaxnreg works on aligned groups of 4 warps):
+//   warps 0-3   TMA producer, MMA issuer, signalling warp, (idle)        32 registers per thread
+//   warps 4-7   epilogue (TMEM lane quarter = warp & 3)                   80
+//   warps 8-19  quantisers                                               120
+// The kernel is launched at 96 registers per thread (640 threads: 61440 registers, the pool setmaxnreg moves
+// registers within -- asking for more than the pool holds blocks forever): 128 x (32 + 80) + 384 x 120 = 60416.
+constexpr int kQuantWarps = 12;
+constexpr int kFirstQuantWarp = 8;
+constexpr int kFThreads = 32 * (kFirstQuantWarp + kQuantWarps);
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+constexpr int kCtr = 16;               // counters per direction (>= ring depth)
+constexpr int kMaxRing = 8;
+
+struct ParamsF {
+  const Tile8* tiles;    // the tiles of this round
+  int n_units;           // tiles x S (<= clusters)
+  int S;                 // frame splits per tile
+  int64_t pairs;         // lagged pairs (M)
+  int Wf, R, n_win;      // frames per window, ring depth, windows
+  int share_stages;      // stages of 128 frames per unit and window = Wf / S / 128
+  int f;
+  double* S0;
+  double* St;
+  const double* scale;
+  // quantiser
+  const float* X;
+  int64_t ld;
+  int lag;               // 0: no lagged rows (PCA)
+  const float* shift;
+  const float* mul;
+  int8_t* planes;        // [set][digit][feature][R * Wf]
+  int64_t wring;         // bytes per feature row of the ring (allocation stride, >= R * Wf)
+  int flo, fhi;          // features this round needs
+  int fg0, n_fg;         // first group of 32 features (absolute index) and number of groups
+  int lanes;             // quantiser warps per feature group
+  int own_lo, own_hi;    // features whose column sums this round accumulates
+  int store_z, store_u;
+  long long* qsum_t;
+  long long* qsum_lag;
+  int* info;
+  int vec4;
+  int ready_target;      // CTAs with at least one active quantiser warp
+  int* ready;            // [kCtr]
+  int* done;             // [kCtr]
+  int dbg;               // diagnostics (DCG_I8_DBG): 1 = quantisers skip their items, 2 = no TMA / MMA, 4 = no fences
+};
+
+// spin on a counter with relaxed loads (an acquire load invalidates L1 on every poll); one fence after the wait
+__device__ __forceinline__ int ld_relaxed_gpu(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void wait_counter_gpu(const int* p, int target, unsigned ns) {
+  while (ld_relaxed_gpu(p) < target) __nanosleep(ns);
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+}
+__device__ __forceinline__ void red_release_gpu(int* p) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// stages of 128 frames that unit split `split` contracts in window w
+__device__ __forceinline__ int win_stages(const ParamsF& p, int w, int split) {
+  const int64_t valid = p.pairs - (int64_t)w * p.Wf;                       // > 0; may exceed Wf
+  const int64_t rem = (valid < p.Wf ? valid : (int64_t)p.Wf) - (int64_t)split * p.share_stages * kStageFrames;
+  if (rem <= 0) return 0;
+  const int64_t st = (rem + kStageFrames - 1) / kStageFrames;
+  return (int)(st < p.share_stages ? st : p.share_stages);
+}
+
+// q + kDigitBias by the float "magic number" rounding (RN-even like __float2int_rn, on the full-rate FP pipe):
+// |y| <= kQMax < 2^22, so y + 1.5 2^23 has unit spacing and its mantissa bits are the integer.
+constexpr int kDigitBias = 0x8080;
+// y = (x - c) 2^e as ONE fused multiply-add, x 2^e - c 2^e: both products are exact (i8_prep_kernel keeps c 2^e
+// finite), so the single rounding is the rounding of the reference's float32 subtraction, scaled.
+// The symmetric clamp is one instruction (min of the magnitudes, sign of y).
+__device__ __forceinline__ float clamp_sym(float y) {
+  float r;
+  asm("min.xorsign.abs.f32 %0, %1, %2;" : "=f"(r) : "f"(y), "f"((float)kQMax));
+  return r;
+}
+__device__ __forceinline__ float max3_abs(float a, float y0, float y1) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(fabsf(y0)), "f"(fabsf(y1)));
+  return r;
+}
+__device__ __forceinline__ int quantize_biased(float y) {
+  return __float_as_int(clamp_sym(y) + 12582912.f) - (0x4B400000 - kDigitBias);
+}
+// balanced digits of four biased integers q' = q + 0x8080 (digits4 above adds 128 / 32896 per digit):
+//   d0 = byte 0 of q = byte 0 of q' with its top bit flipped, d1 = byte 1 of q + 128 = byte 1 of q' with its top
+//   bit flipped, d2 = byte 2 of q + 32896 = byte 2 of q'
+__device__ __forceinline__ void digits4_biased(int a, int b, int c, int d, uint32_t& w0, uint32_t& w1, uint32_t& w2) {
+  w0 = pack_byte<0>(a, b, c, d) ^ 0x80808080u;
+  w1 = pack_byte<1>(a, b, c, d) ^ 0x80808080u;
+  w2 = pack_byte<2>(a, b, c, d);
+}
+
+template <bool WITH_LAG>
+__device__ __forceinline__ void quantize_window_item(const ParamsF& p, int w, int ch, int feat, int lane,
+                                                     const float (&c)[4], const float (&m)[4], const bool (&in_f)[4],
+                                                     const bool (&st_ok)[4], long long (&acc_t)[4],
+                                                     long long (&acc_l)[4], int& clamped) {
+  const int g = lane >> 3;                                      // group of 8 frames
+  const int64_t t0 = (int64_t)w * p.Wf + ch * 32 + 8 * g;       // first pair of this thread
+  float x[8][4], xl[8][4];
+  const size_t lag_off = (size_t)p.lag * (size_t)p.ld;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t t = t0 + i;
+    const bool live = t < p.pairs;
+    const float* px = p.X + (size_t)t * (size_t)p.ld + feat;
+    if (p.dbg & 32) {
+#pragma unroll
+      for (int v = 0; v < 4; ++v) { x[i][v] = c[v] + (float)i; xl[i][v] = c[v] - (float)i; }
+    } else if (live && p.vec4 && in_f[3]) {
+      const float4 a = (p.dbg & 64) ? ldg_stream4(px) : __ldg(reinterpret_cast<const float4*>(px));   // L1-allocating: the lagged rows of the same warp merge in L1
+      x[i][0] = a.x; x[i][1] = a.y; x[i][2] = a.z; x[i][3] = a.w;
+      if (WITH_LAG) {
+        const float4 b = (p.dbg & 64) ? ldg_stream4(px + lag_off) : __ldg(reinterpret_cast<const float4*>(px + ((p.dbg & 16) ? 0 : lag_off)));
+        xl[i][0] = b.x; xl[i][1] = b.y; xl[i][2] = b.z; xl[i][3] = b.w;
+      }
+    } else {
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        x[i][v] = (live && in_f[v]) ? ldg_stream1(px + v) : c[v];
+        if (WITH_LAG) xl[i][v] = (live && in_f[v]) ? ldg_stream1(px + lag_off + v) : c[v];
+      }
+    }
+  }
+  const size_t plane_stride = (size_t)p.f * (size_t)p.wring;
+  const size_t col = (size_t)(w % p.R) * (size_t)p.Wf + (size_t)ch * 32 + 8 * g;
+  float amax = 0.f;
+  const float ncm[4] = {-c[0] * m[0], -c[1] * m[1], -c[2] * m[2], -c[3] * m[3]};
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    // biased integers q + 0x8080 (quantize_biased): the digit bytes are bytes 0, 1 (top bit flipped) and 2
+    int q[8], u[8];
+    int ps = 0, pl = 0;                                          // |q| < 2^22: eight of them fit an int
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float y = fmaf(x[i][v], m[v], ncm[v]);
+      q[i] = quantize_biased(y);
+      ps += q[i];
+      if (WITH_LAG) {
+        const float yl = fmaf(xl[i][v], m[v], ncm[v]);
+        amax = max3_abs(amax, y, yl);
+        const int ql = quantize_biased(yl);
+        pl += ql;
+        u[i] = q[i] + ql - kDigitBias;
+      } else {
+        amax = fmaxf(amax, fabsf(y));
+      }
+    }
+    acc_t[v] += ps - 8 * kDigitBias;
+    if (WITH_LAG) acc_l[v] += pl - 8 * kDigitBias;
+    if (!st_ok[v] || (p.dbg & 8)) continue;
+    int8_t* dst = p.planes + (size_t)(feat + v) * (size_t)p.wring + col;
+    if (p.store_z) {
+      uint32_t a0, a1, a2, b0, b1, b2;
+      digits4_biased(q[0], q[1], q[2], q[3], a0, a1, a2);
+      digits4_biased(q[4], q[5], q[6], q[7], b0, b1, b2);
+      *reinterpret_cast<uint2*>(dst) = make_uint2(a0, b0);
+      *reinterpret_cast<uint2*>(dst + plane_stride) = make_uint2(a1, b1);
+      *reinterpret_cast<uint2*>(dst + 2 * plane_stride) = make_uint2(a2, b2);
+    }
+    if (WITH_LAG && p.store_u) {
+      uint32_t a0, a1, a2, b0, b1, b2;
+      digits4_biased(u[0], u[1], u[2], u[3], a0, a1, a2);
+      digits4_biased(u[4], u[5], u[6], u[7], b0, b1, b2);
+      *reinterpret_cast<uint2*>(dst + 3 * plane_stride) = make_uint2(a0, b0);
+      *reinterpret_cast<uint2*>(dst + 4 * plane_stride) = make_uint2(a1, b1);
+      *reinterpret_cast<uint2*>(dst + 5 * plane_stride) = make_uint2(a2, b2);
+    }
+  }
+  clamped += amax > (float)kQMax + 0.5f;                        // groups of 8 x 4 values that held a clamped one
+}
+
+template <bool WITH_LAG>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFThreads, 1)
+cov_i8_fused_kernel(const __grid_constant__ CUtensorMap map_a,      // ring [set][digit][feature][frame], box 128 x 128
+                    const __grid_constant__ CUtensorMap map_b,      // same tensor, box 128 x 64
+                    const ParamsF p) {
+  extern __shared__ unsigned char smem_raw8f[];
+  const uint32_t smem_base = (smem_u32(smem_raw8f) + 1023u) & ~1023u;
+  __shared__ uint64_t full_bar[8], empty_bar[8], acc_full, acc_empty;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ double epi_smem[4 * 32 * 9];
+  __shared__ int q_cnt[kCtr];          // quantiser warps of this CTA that are through window w (slot w % kCtr, monotonic)
+  __shared__ int q_can_write;          // last window whose ring slot may be written
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank8();
+  constexpr int N = kMaxN;
+  constexpr uint32_t pb = (uint32_t)plane_b_bytes(N), sb = (uint32_t)stage_bytes(N);
+  constexpr int NS = 3;
+
+  if (tid == 0) {
+    for (int i = 0; i < NS; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(&acc_full, 1);
+    mbar_init(&acc_empty, 2 * 4);
+    fence_barrier_init();
+    for (int i = 0; i < kCtr; ++i) q_cnt[i] = 0;
+    q_can_write = p.R - 1;
+  }
+  if (warp == 1) tmem_alloc2_8(&tmem_base_s, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync8();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  const int unit = (int)(blockIdx.x >> 1);
+  const bool has_unit = unit < p.n_units;
+  const int split = has_unit ? unit % p.S : 0;
+  Tile8 td = p.tiles[has_unit ? unit / p.S : 0];
+  const int max_acc = kMaxItemFrames / kStageFrames;             // stages per int32 accumulation
+
+  const int n_qw = p.n_fg * p.lanes;                               // active quantiser warps of the grid
+  const int qw0 = (int)blockIdx.x * kQuantWarps;
+  const int n_act = n_qw - qw0 < 0 ? 0 : (n_qw - qw0 > kQuantWarps ? kQuantWarps : n_qw - qw0);   // ... of this CTA
+
+  if (warp < 4) {
+  setmaxnreg_dec<32>();
+  if (warp == 0) {
+    // ===================== TMA producer (one lane per CTA) =============================================
+    if (lane == 0 && has_unit) {
+      const int set = td.kind;
+      const int ia_t = rank ? td.ia1 : td.ia0;
+      const int ia = ia_t < 0 ? p.f : ia_t, jb = td.j0 + (int)rank * (N / 2);
+      const int n_q = p.ready_target;                             // CTAs that release a window
+      uint32_t g = 0;
+      for (int w = 0; w < p.n_win; ++w) {
+        const int nS = win_stages(p, w, split);
+        if (nS == 0) continue;
+        const int target = n_q * (w / kCtr + 1);
+        wait_counter_gpu(p.ready + (w % kCtr), target, 100);
+        fence_proxy_async_all();                                  // generic-proxy writes of the quantisers -> TMA reads
+        const int base = (w % p.R) * p.Wf + split * p.share_stages * kStageFrames;
+        for (int s = 0; s < nS && !(p.dbg & 2); ++s, ++g) {
+          const uint32_t slot = g % NS;
+          mbar_wait(&empty_bar[slot], ((g / NS) & 1) ^ 1);
+          const uint32_t bar = smem_u32(&full_bar[slot]) & 0xFEFFFFFFu;
+          if (rank == 0) mbar_expect_tx(&full_bar[slot], 2 * sb);
+          const uint32_t dst = smem_base + slot * sb;
+          const int t = base + s * kStageFrames;
+#pragma unroll
+          for (int pl = 0; pl < 3; ++pl) tma_load_4d(dst + pl * kPlaneA, &map_a, bar, t, ia, pl, set);
+#pragma unroll
+          for (int pl = 0; pl < 3; ++pl) tma_load_4d(dst + 3 * kPlaneA + pl * pb, &map_b, bar, t, jb, pl, set);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA) =====================================================
+    if (rank == 0 && has_unit) {
+      constexpr uint32_t idesc = make_idesc_i8(kTileM, N);
+      const uint32_t accA = tmem, accB = tmem + N, accC = tmem + 2 * N, accD = tmem + 3 * N;
+      uint32_t g = 0, flushes = 0;
+      int acc = 0;
+      for (int w = 0; w < p.n_win; ++w) {
+        const int nS = win_stages(p, w, split);
+        if (acc == 0 && nS > 0) {
+          mbar_wait_cluster8(&acc_empty, (flushes & 1) ^ 1);
+          tc_fence_after();
+        }
+        for (int s = 0; s < nS && !(p.dbg & 2); ++s, ++g) {
+          const uint32_t slot = g % NS;
+          mbar_wait_cluster8(&full_bar[slot], (g / NS) & 1);
+          tc_fence_after();
+          if (elect_one_sync()) {
+            const uint32_t st = smem_base + slot * sb;
+            const uint64_t a0 = make_smem_desc_sw128(st), a1 = make_smem_desc_sw128(st + kPlaneA),
+                           a2 = make_smem_desc_sw128(st + 2 * kPlaneA);
+            const uint32_t sbb = st + 3 * kPlaneA;
+            const uint64_t b0 = make_smem_desc_sw128(sbb), b1 = make_smem_desc_sw128(sbb + pb),
+                           b2 = make_smem_desc_sw128(sbb + 2 * pb);
+#pragma unroll
+            for (int h = 0; h < kKSteps; ++h) {
+              const uint64_t o = (uint64_t)(h * 32 >> 4);
+              const uint32_t first = (acc == 0 && s == 0 && h == 0) ? 0u : 1u;
+              mma2_i8_ss(accA, a2 + o, b2 + o, idesc, first);
+              mma2_i8_ss(accB, a2 + o, b1 + o, idesc, first);
+              mma2_i8_ss(accB, a1 + o, b2 + o, idesc, 1u);
+              mma2_i8_ss(accC, a2 + o, b0 + o, idesc, first);
+              mma2_i8_ss(accC, a1 + o, b1 + o, idesc, 1u);
+              mma2_i8_ss(accC, a0 + o, b2 + o, idesc, 1u);
+              mma2_i8_ss(accD, a1 + o, b0 + o, idesc, first);
+              mma2_i8_ss(accD, a0 + o, b1 + o, idesc, 1u);
+            }
+            mma2_commit_both8(&empty_bar[slot]);
+          }
+          __syncwarp();
+        }
+        // every load of this cluster from ring slot w % R has landed: the slot may be overwritten
+        if (lane == 0) red_release_gpu(p.done + (w % kCtr));
+        acc += nS;
+        const bool flush = acc > 0 && (w == p.n_win - 1 || acc + p.share_stages > max_acc);
+        if (flush) {
+          if (elect_one_sync()) mma2_commit_both8(&acc_full);
+          __syncwarp();
+          ++flushes;
+          acc = 0;
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== signalling warp of the quantisers ===========================================
+      if (lane == 0 && n_act > 0) {
+        int wa = p.R, wb = 0;                                      // next window to permit / to release
+        while (wb < p.n_win) {
+          bool progress = false;
+          if (wa < p.n_win) {
+            const int wd = wa - p.R;
+            if (ld_relaxed_gpu(p.done + (wd % kCtr)) >= p.n_units * (wd / kCtr + 1)) {
+              asm volatile("fence.acq_rel.gpu;" ::: "memory");
+              *(volatile int*)&q_can_write = wa;
+              ++wa;
+              progress = true;
+            }
+          }
+          if (*(volatile int*)&q_cnt[wb % kCtr] >= n_act * (wb / kCtr + 1)) {
+            if (!(p.dbg & 4)) __threadfence();                     // cumulative: covers the quantisers' stores
+            red_release_gpu(p.ready + (wb % kCtr));
+            ++wb;
+            progress = true;
+          }
+          if (!progress) __nanosleep(100);
+        }
+      }
+  }
+  } else if (warp < kFirstQuantWarp) {
+  setmaxnreg_dec<80>();
+  {
+    // ===================== epilogue: int32 accumulators -> FP64 result ==================================
+    if (has_unit) {
+      const int q = warp & 3;
+      const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+      const int ia_t = rank ? td.ia1 : td.ia0;
+      const bool transposed = (rank ? td.tr1 : td.tr0) != 0;
+      const int row0 = ia_t + 32 * q;
+      const int gi_row = row0 + lane;
+      const bool row_ok = ia_t >= 0 && gi_row < td.hi;
+      const double si = row_ok ? p.scale[gi_row] : 0.0;
+      double* sE = epi_smem + (warp - 4) * (32 * 9);
+      double* outm = td.kind == 0 ? p.S0 : p.St;
+      uint32_t flushes = 0;
+      int acc = 0;
+      for (int w = 0; w < p.n_win; ++w) {
+        acc += win_stages(p, w, split);
+        const bool flush = acc > 0 && (w == p.n_win - 1 || acc + p.share_stages > max_acc);
+        if (!flush) continue;
+        acc = 0;
+        mbar_wait(&acc_full, flushes & 1);
+        ++flushes;
+        tc_fence_after();
+        for (int c0 = 0; c0 < N && ia_t >= 0; c0 += 8) {
+          const int cb = td.j0 + c0;                               // first column of this group of 8
+          if (cb >= td.hi) break;                                  // beyond the edge (warp-uniform)
+          if (!transposed && cb + 7 < row0) continue;              // wholly below the diagonal (warp-uniform)
+          uint32_t va[8], vb[8], vc[8], vd[8];
+          tmem_ld_x8(tmem + lane_base + c0, va);
+          tmem_ld_x8(tmem + N + lane_base + c0, vb);
+          tmem_ld_x8(tmem + 2 * N + lane_base + c0, vc);
+          tmem_ld_x8(tmem + 3 * N + lane_base + c0, vd);
+          tmem_ld_wait();
+          double v8[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int gj = cb + j;
+            const double v = (double)(int)va[j] * 4294967296.0 + (double)(int)vb[j] * 16777216.0 +
+                             (double)(int)vc[j] * 65536.0 + (double)(int)vd[j] * 256.0;
+            v8[j] = gj < td.hi ? v * si * p.scale[gj] : 0.0;
+          }
+          if (transposed) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (row_ok && cb + j < td.hi) atomicAdd(outm + (size_t)(cb + j) * p.f + gi_row, v8[j]);
+            continue;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) sE[lane * 9 + j] = v8[j];
+          __syncwarp();
+          const int col = lane & 7, gj = cb + col;
+#pragma unroll
+          for (int rr = 0; rr < 8; ++rr) {
+            const int row = 4 * rr + (lane >> 3), gi = row0 + row;
+            if (gi < td.hi && gj < td.hi && gj >= gi) atomicAdd(outm + (size_t)gi * p.f + gj, sE[row * 9 + col]);
+          }
+          __syncwarp();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote8(&acc_empty, 0);
+      }
+    }
+  }
+  } else {
+  setmaxnreg_inc<120>();
+  {
+    // ===================== quantisers ===================================================================
+    if (qw0 + (warp - kFirstQuantWarp) < n_qw) {
+      const int qw = qw0 + (warp - kFirstQuantWarp);
+      const int fgi = qw % p.n_fg, ln = qw / p.n_fg;
+      const int feat = (p.fg0 + fgi) * 32 + 4 * (lane & 7);
+      float c[4], m[4];
+      bool in_f[4], st_ok[4], own[4];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        in_f[v] = feat + v < p.f;
+        st_ok[v] = in_f[v] && feat + v >= p.flo && feat + v < p.fhi;
+        own[v] = in_f[v] && feat + v >= p.own_lo && feat + v < p.own_hi;
+        c[v] = in_f[v] ? p.shift[feat + v] : 0.f;
+        m[v] = in_f[v] ? p.mul[feat + v] : 0.f;
+      }
+      long long acc_t[4] = {0, 0, 0, 0}, acc_l[4] = {0, 0, 0, 0};
+      int clamped = 0;
+      const int chunks = p.Wf / 32;
+      // chunks rotate over the lanes from window to window (the load evens out across windows); frames at and
+      // beyond `pairs` are written as zeros up to the end of the last 128-frame stage that is read
+      auto live_chunks_of = [&](int w) {
+        const int64_t valid = p.pairs - (int64_t)w * p.Wf;
+        return valid >= p.Wf ? chunks : (int)((valid + kStageFrames - 1) / kStageFrames) * (kStageFrames / 32);
+      };
+      auto first_chunk_of = [&](int w) {
+        return (int)(((int64_t)ln - ((int64_t)w * chunks) % p.lanes + p.lanes) % p.lanes);
+      };
+      // L2 prefetch of the rows of the items kPrefetchAhead ahead (one row of 32 features = 128 bytes per lane):
+      // with 8 warps per SM, each loading, computing and storing in turn, DRAM latency is otherwise exposed
+      const float* pf_base = p.X + (size_t)(p.fg0 + fgi) * 32;
+      const int64_t n_rows = p.pairs + p.lag;
+      const bool pf_full = (p.fg0 + fgi) * 32 + 31 < p.f;
+      auto prefetch_item = [&](int w, int ch) {
+        const int64_t row = (int64_t)w * p.Wf + ch * 32 + lane;
+        if (row >= n_rows || (p.fg0 + fgi) * 32 >= p.f) return;
+        const float* a = pf_base + (size_t)row * (size_t)p.ld;
+        if (p.vec4 && pf_full) {
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], 128;" ::"l"(a) : "memory");
+        } else {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+          if (pf_full) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + 31));
+        }
+      };
+      // item cursor: the next (w, ch) of this warp with ch < live(w); w = n_win at the end
+      auto next_item = [&](int& w, int& ch) {
+        ch += p.lanes;
+        while (w < p.n_win && ch >= live_chunks_of(w)) {
+          ++w;
+          if (w < p.n_win) ch = first_chunk_of(w);
+        }
+      };
+      constexpr int kPrefetchAhead = 2;
+      int pw = 0, pch = first_chunk_of(0) - p.lanes;
+      next_item(pw, pch);
+      for (int i = 0; i < kPrefetchAhead && pw < p.n_win; ++i) {
+        prefetch_item(pw, pch);
+        next_item(pw, pch);
+      }
+      for (int w = 0; w < p.n_win; ++w) {
+        const int live = live_chunks_of(w);
+        if (w >= p.R) {
+          while (*(volatile int*)&q_can_write < w) __nanosleep(64);
+          __threadfence_block();
+        }
+        for (int ch = first_chunk_of(w); ch < live && !(p.dbg & 1); ch += p.lanes) {
+          if (pw < p.n_win) {
+            prefetch_item(pw, pch);
+            next_item(pw, pch);
+          }
+          quantize_window_item<WITH_LAG>(p, w, ch, feat, lane, c, m, in_f, st_ok, acc_t, acc_l, clamped);
+        }
+        __syncwarp();
+        if (lane == 0) {
+          __threadfence_block();
+          atomicAdd_block(&q_cnt[w % kCtr], 1);
+        }
+      }
+      if (p.qsum_t) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          long long a = acc_t[v], b = acc_l[v];
+          a += __shfl_xor_sync(0xffffffffu, a, 8);  a += __shfl_xor_sync(0xffffffffu, a, 16);
+          b += __shfl_xor_sync(0xffffffffu, b, 8);  b += __shfl_xor_sync(0xffffffffu, b, 16);
+          if (lane < 8 && own[v]) {
+            atomicAdd((unsigned long long*)p.qsum_t + feat + v, (unsigned long long)a);
+            if (WITH_LAG) atomicAdd((unsigned long long*)p.qsum_lag + feat + v, (unsigned long long)b);
+          }
+        }
+      }
+      if (clamped && p.info) atomicAdd(p.info, clamped);
+    }
+  }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync8();
+  if (warp == 1) tmem_dealloc2_8(tmem, 512);
+}
+
 // ---- host side ----------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -673,27 +1199,94 @@ struct Timing8 {
 Timing8 g_timing;                            // diagnostics only: one stream, one thread
 
 struct Layout8 {
-  size_t tiles, shift, mul, scale, qsum, planes, total;
+  size_t tiles, shift, mul, scale, qsum, counters, planes, total;
   int64_t wf, wpad;
   int n_tiles_max, n_sets;
+  bool fused;            // the fused quantise + contraction kernel (ring of digit planes in L2)
+  int ring;              // ring depth R
+  int64_t ring_budget;   // bytes of digit planes that may be live at once
+  int64_t wring;         // bytes per feature row of the ring
 };
+
+constexpr int kMaxRounds = 64;
+constexpr int kAssumedClusters = 64;   // the fused plan needs at least this many co-resident clusters
+
+// The fused kernel applies to the 128-wide tile plan, and pays off where the contraction is the longer of the two
+// phases: its 8 quantiser warps per SM need 4.3 ps per value (the stand-alone quantise kernel, at full occupancy,
+// 2.35 ps) against 11 ns per frame and tile-per-cluster for the tensor pipe (measured at C2).  Block-diagonal
+// level-1 sums of hTICA (C3: 100 tiles for 4950 features) are quantise-bound and stay on the two-kernel path.
+// DCG_I8_FUSED: 0 = never, 1 = by this rule (default), 2 = whenever the plan allows it.
+bool fused_applies(int f, int lag, int block) {
+  const int64_t mode = env_i64("DCG_I8_FUSED", 1);
+  if (mode == 0) return false;
+  if (tile_width(f, block) != kHalfM) return false;
+  if (ceil_div(f, 32) + 1 > 2 * kAssumedClusters * kQuantWarps) return false;
+  const int n_tiles = enum_tiles8(f, block, kHalfM, true, lag > 0, nullptr);
+  if (n_tiles > kMaxRounds * kAssumedClusters) return false;
+  if (mode >= 2) return true;
+  return (double)n_tiles * 35.0 >= (double)f * (lag > 0 ? 1.0 : 0.55);
+}
 
 Layout8 layout8(int64_t n_rows, int f, int lag, int block) {
   Layout8 L;
   const int N = tile_width(f, block);
   L.n_tiles_max = enum_tiles8(f, block, N, true, true, nullptr);
   L.n_sets = lag > 0 ? 2 : 1;
-  L.wf = window_frames(n_rows, f, lag);
-  L.wpad = (int64_t)align_up((size_t)L.wf, 128);
+  L.fused = fused_applies(f, lag, block);
+  L.ring = (int)std::min<int64_t>(std::max<int64_t>(env_i64("DCG_I8_RING", 4), 2), kMaxRing);
+  L.ring_budget = std::max<int64_t>(env_i64("DCG_I8_RING_BYTES", (int64_t)48 << 20), 1 << 20);
+  L.wring = 0;
+  if (L.fused) {
+    L.wf = 0;
+    // widest window the plan can ask for: one stage per frame split, or the budget on a narrow matrix
+    const int one_kind = std::max(1, enum_tiles8(f, block, N, true, false, nullptr));
+    const int s_max = std::max(1, (kNumSMs / 2) / std::min(one_kind, kNumSMs / 2));
+    const int64_t by_budget = L.ring_budget / (3 * L.n_sets * (int64_t)std::min(f, 1024));
+    L.wring = (int64_t)align_up((size_t)std::max<int64_t>((int64_t)L.ring * kStageFrames * s_max, by_budget), 128);
+    L.wpad = L.wring;
+  } else {
+    L.wf = window_frames(n_rows, f, lag);
+    L.wpad = (int64_t)align_up((size_t)L.wf, 128);
+  }
   size_t o = 256;
   L.tiles = o; o += align_up((size_t)L.n_tiles_max * sizeof(Tile8), 256);
   L.shift = o; o += align_up((size_t)f * 4, 256);
   L.mul = o; o += align_up((size_t)f * 4, 256);
   L.scale = o; o += align_up((size_t)f * 8, 256);
   L.qsum = o; o += align_up((size_t)f * 16, 256);
+  L.counters = o; o += align_up((size_t)kMaxRounds * 2 * kCtr * sizeof(int), 256);
   L.planes = align_up(o, 1024); o = L.planes + (size_t)3 * L.n_sets * (size_t)f * (size_t)L.wpad;
   L.total = o + 1024;
   return L;
+}
+
+// clusters of the fused kernel that can be resident at once (they wait on each other), per device
+int fused_clusters(size_t smem) {
+  static int cached[64];
+  static bool have[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  if (!have[dev]) {
+    int best = kNumSMs / 2;
+    for (int v = 0; v < 2; ++v) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(kNumSMs, 1, 1);
+      cfg.blockDim = dim3(kFThreads, 1, 1);
+      cfg.dynamicSmemBytes = smem;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      int n = 0;
+      const void* fn = v ? (const void*)cov_i8_fused_kernel<true> : (const void*)cov_i8_fused_kernel<false>;
+      if (cudaOccupancyMaxActiveClusters(&n, fn, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+      best = std::min(best, n);
+    }
+    cached[dev] = best;
+    have[dev] = true;
+  }
+  return cached[dev];
 }
 
 }  // namespace
@@ -775,6 +1368,89 @@ extern "C" int dcg_cov_lag_i8_f32(const float* X, int64_t n_rows, int f, int64_t
   plan8_kernel<<<1, 32, 0, st>>>(d_tiles, f, block, N, S0 != nullptr, with_u);
   DCG_I8_STEP("plan");
 
+  const bool lag_rows_f = lag > 0;
+  if (L.fused) {
+    // ---- fused path: per round one persistent launch that quantises and contracts -----------------------
+    const size_t fsmem = (size_t)3 * stage_bytes(kMaxN) + 1024;
+    DCG_CUDA_TRY(ensure_dynamic_smem((const void*)cov_i8_fused_kernel<true>, fsmem));
+    DCG_CUDA_TRY(ensure_dynamic_smem((const void*)cov_i8_fused_kernel<false>, fsmem));
+    const int nC = (int)std::min<int64_t>(fused_clusters(fsmem), env_i64("DCG_I8_CLUSTERS", kNumSMs / 2));
+    if (nC < 1) return DCG_E_ARCH;
+    std::vector<Tile8> tiles((size_t)std::max(n_tiles, 1));
+    enum_tiles8(f, block, N, S0 != nullptr, with_u, tiles.data());
+    if (ceil_div(n_tiles, nC) > kMaxRounds) return DCG_E_SHAPE;
+    int* d_ctr = (int*)(base + L.counters);
+    DCG_CUDA_TRY(cudaMemsetAsync(d_ctr, 0, (size_t)kMaxRounds * 2 * kCtr * sizeof(int), st));
+    const int vec4f = row_vec_width(X, ld) == 4 ? 1 : 0;
+    const bool timedf = g_timing.on && g_timing.n < 64;
+    if (timedf) { cudaEventRecord(g_timing.q0[g_timing.n], st); cudaEventRecord(g_timing.q1[g_timing.n], st); }
+    int own_from = 0;                                   // column sums: every feature is owned by exactly one round
+    const int n_rounds = std::max<int>(1, (int)ceil_div(n_tiles, nC));
+    for (int r = 0; r < n_rounds; ++r) {
+      const int t0 = r * nC, nt = std::min(nC, n_tiles - t0);
+      ParamsF p{};
+      int flo = 0, fhi = f, sz = 0, su = 0;
+      if (nt > 0) {
+        flo = f; fhi = 0;
+        for (int i = t0; i < t0 + nt; ++i) {
+          const Tile8& t = tiles[(size_t)i];
+          const int lo = std::min(t.ia0, t.j0), rows_hi = (t.ia1 >= 0 ? std::max(t.ia0, t.ia1) : t.ia0) + kHalfM;
+          flo = std::min(flo, lo);
+          fhi = std::max(fhi, std::min(t.hi, std::max(rows_hi, t.j0 + kMaxN)));
+          (t.kind == 0 ? sz : su) = 1;
+        }
+      }
+      // the last round also takes the features no tile needs (column sums only: nothing is stored for them)
+      const bool last = r == n_rounds - 1;
+      const int q_lo = std::min(flo, own_from), q_hi = last ? f : fhi;
+      p.tiles = d_tiles + t0;
+      p.S = nt > 0 ? std::max(1, nC / nt) : 1;
+      p.n_units = std::max(nt, 0) * p.S;
+      p.pairs = M;
+      p.R = L.ring;
+      p.fg0 = q_lo / 32;
+      p.n_fg = (int)ceil_div(std::max(q_hi, q_lo + 1), 32) - p.fg0;
+      p.lanes = std::max(1, 2 * nC * kQuantWarps / p.n_fg);
+      if (p.n_fg > 2 * nC * kQuantWarps) return DCG_E_SHAPE;
+      {
+        const int64_t unit_frames = (int64_t)kStageFrames * p.S;
+        const int64_t by_l2 = L.ring_budget / (3 * (int64_t)L.n_sets * 32 * p.n_fg * p.R);
+        int64_t k = std::min<int64_t>(L.wring / p.R, by_l2) / unit_frames;
+        k = std::min<int64_t>(k, kMaxItemFrames / kStageFrames);
+        k = std::min<int64_t>(k, ceil_div(M, unit_frames));
+        k = std::max<int64_t>(k, 1);
+        k = std::max<int64_t>(1, env_i64("DCG_I8_WINDOW_STAGES", k));
+        p.Wf = (int)(k * unit_frames);
+        p.share_stages = (int)k;
+        if ((int64_t)p.R * p.Wf > L.wring) return DCG_E_WORKSPACE;
+      }
+      p.n_win = (int)ceil_div(M, p.Wf);
+      p.f = f; p.S0 = S0; p.St = St; p.scale = d_scale;
+      p.X = X; p.ld = ld; p.lag = lag; p.shift = d_shift; p.mul = d_mul;
+      p.planes = d_planes; p.wring = L.wring;
+      p.flo = flo; p.fhi = fhi;
+      p.own_lo = own_from; p.own_hi = q_hi;
+      own_from = std::max(own_from, q_hi);
+      p.store_z = sz; p.store_u = su;
+      p.qsum_t = d_qsum; p.qsum_lag = d_qsum + f; p.info = info; p.vec4 = vec4f;
+      p.ready = d_ctr + (size_t)r * 2 * kCtr; p.done = p.ready + kCtr;
+      p.dbg = (int)env_i64("DCG_I8_DBG", 0);
+      p.ready_target = (int)ceil_div((int64_t)p.n_fg * p.lanes, kQuantWarps);
+      CUtensorMap ma, mb;
+      int rc = make_plane_map(&ma, d_planes, (int64_t)p.R * p.Wf, f, L.wring, L.n_sets, kHalfM);
+      if (!rc) rc = make_plane_map(&mb, d_planes, (int64_t)p.R * p.Wf, f, L.wring, L.n_sets, kMaxN / 2);
+      if (rc) return rc;
+      if (getenv("DCG_I8_DEBUG"))
+        fprintf(stderr, "[dcg i8 fused] round %d/%d: tiles %d units %d S %d Wf %d R %d windows %d features [%d,%d) groups %d x lanes %d\n",
+                r, n_rounds, nt, p.n_units, p.S, p.Wf, p.R, p.n_win, flo, fhi, p.n_fg, p.lanes);
+      if (lag_rows_f)
+        cov_i8_fused_kernel<true><<<2 * nC, kFThreads, fsmem, st>>>(ma, mb, p);
+      else
+        cov_i8_fused_kernel<false><<<2 * nC, kFThreads, fsmem, st>>>(ma, mb, p);
+      DCG_I8_STEP("fused");
+    }
+    if (timedf) cudaEventRecord(g_timing.c1[g_timing.n++], st);
+  } else {
   const int ns = num_stages(N);
   const size_t smem = (size_t)ns * stage_bytes(N) + 1024;
   DCG_CUDA_TRY(ensure_dynamic_smem((const void*)cov_i8_kernel, smem));
@@ -818,6 +1494,7 @@ extern "C" int dcg_cov_lag_i8_f32(const float* X, int64_t n_rows, int f, int64_t
     DCG_I8_STEP("contract");
     if (timed) cudaEventRecord(g_timing.c1[g_timing.n++], st);
   }
+  }  // unfused path
   if (colsum_t || colsum_lag) {
     i8_finish_sums_kernel<<<(unsigned)ceil_div(f, 128), 128, 0, st>>>(f, d_scale, d_qsum, d_qsum + f, lag, colsum_t,
                                                                      colsum_lag);

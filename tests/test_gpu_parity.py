@@ -192,6 +192,51 @@ def test_cov_unaligned_rows_and_block_origins(dev, f, ld_pad, block):
     _assert_cov_close(s, oracle.lagged_sums(Z, lag), 1e-5, block=block)
 
 
+@pytest.mark.parametrize("n,f,lag,block,ld_pad,standardise", [
+    (5000, 300, 7, 0, 0, True),            # one round, several frame splits per tile
+    (20011, 1003, 33, 100, 1, True),       # block mode, blocks that start at odd columns, padded rows, lag > 32
+    (9000, 331, 0, 0, 0, True),            # lag 0 (PCA): Z planes only
+    (12000, 2000, 10, 0, 0, True),         # 136 tiles: two rounds of the persistent kernel
+    (6000, 4950, 10, 495, 2, True),        # the C3 level-1 plan: 100 tiles, rounds that quantise feature sub-ranges
+    (3001, 1000, 3, 0, 0, False),          # raw features (mode None), a last window that is partly empty
+])
+def test_cov_exact_engine_fused_kernel_equals_two_kernel_path(dev, monkeypatch, n, f, lag, block, ld_pad, standardise):
+    """tc_i8x3 has two implementations of the same integer arithmetic: quantise kernel + contraction kernel
+    (planes in HBM), and the fused persistent kernel (quantiser warps -> L2-resident ring -> TMA -> tcgen05).
+    Both must give the float64 checker's sums to 1e-5 and each other's to rounding of the FP64 adds; the column
+    sums are integer totals and must be IDENTICAL."""
+    from deep_cartograph_b200 import ops
+    from oracle import float64_device as f64
+    X = synth_features(n, f, seed=n + f)
+    buf = torch.zeros((n, f + ld_pad), dtype=torch.float32, device=dev)
+    buf[:, :f] = torch.from_numpy(X).to(dev)
+    Xd = buf[:, :f]
+    mean = rng = None
+    if standardise:
+        st = ops.column_stats(Xd)
+        mean = st["mean"].float()
+        rng = torch.sqrt(st["m2"] / (n - 1)).float()
+    out = {}
+    for mode in ("2", "0"):                # 2 = fused whenever the tile plan allows it, 0 = never
+        monkeypatch.setenv("DCG_I8_FUSED", mode)
+        out[mode] = ops.lagged_covariance(Xd, lag, mean, rng, block=block, engine="tc_i8x3")
+        torch.cuda.synchronize()
+        assert int(out[mode]["clamped"].item()) == 0
+    ref = f64.lagged_sums(Xd, lag, mean, rng)
+    mask = torch.ones((f, f), dtype=torch.bool, device=dev).triu()
+    if block:
+        blk = torch.arange(f, device=dev) // block
+        mask &= blk[:, None] == blk[None, :]
+    for k in ("S0", "St"):
+        if lag == 0 and k == "St":
+            continue
+        r = ref[k] if k == "S0" else 0.5 * (ref[k] + ref[k].T)
+        a, b, r = (torch.where(mask, t, torch.zeros_like(t)) for t in (out["2"][k], out["0"][k], r))
+        assert float((a - r).norm() / r.norm()) < 1e-6, k
+        assert float((a - b).abs().max() / b.abs().max()) < 1e-14, k
+    assert torch.equal(out["2"]["a"], out["0"]["a"]) and torch.equal(out["2"]["b"], out["0"]["b"])
+
+
 @pytest.mark.parametrize("engine", ["tc_3xf16", "tc_3xtf32"])
 def test_cov_split_precision_edge_columns(dev, engine):
     """Columns that stress the split-precision operands: a constant feature (range -> 1, z = 0), a
