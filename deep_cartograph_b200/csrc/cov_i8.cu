@@ -1443,10 +1443,30 @@ extern "C" int dcg_cov_lag_i8_f32(const float* X, int64_t n_rows, int f, int64_t
       if (getenv("DCG_I8_DEBUG"))
         fprintf(stderr, "[dcg i8 fused] round %d/%d: tiles %d units %d S %d Wf %d R %d windows %d features [%d,%d) groups %d x lanes %d\n",
                 r, n_rounds, nt, p.n_units, p.S, p.Wf, p.R, p.n_win, flo, fhi, p.n_fg, p.lanes);
-      if (lag_rows_f)
-        cov_i8_fused_kernel<true><<<2 * nC, kFThreads, fsmem, st>>>(ma, mb, p);
-      else
-        cov_i8_fused_kernel<false><<<2 * nC, kFThreads, fsmem, st>>>(ma, mb, p);
+      // Cooperative launch: the CTAs wait on each other, so the grid must become resident as a whole (two
+      // partially resident grids on different streams would otherwise wait for each other's SMs forever).
+      {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * nC, 1, 1);
+        cfg.blockDim = dim3(kFThreads, 1, 1);
+        cfg.dynamicSmemBytes = fsmem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = env_i64("DCG_I8_COOPERATIVE", 1) ? 1 : 0;
+        cudaError_t le = lag_rows_f ? cudaLaunchKernelEx(&cfg, cov_i8_fused_kernel<true>, ma, mb, p)
+                                    : cudaLaunchKernelEx(&cfg, cov_i8_fused_kernel<false>, ma, mb, p);
+        if (le != cudaSuccess && cfg.numAttrs) {           // no cooperative launch of clusters on this driver: plain launch
+          if (getenv("DCG_I8_DEBUG")) fprintf(stderr, "[dcg i8 fused] cooperative launch refused (%s): plain launch\n", cudaGetErrorString(le));
+          cudaGetLastError();
+          cfg.numAttrs = 0;
+          le = lag_rows_f ? cudaLaunchKernelEx(&cfg, cov_i8_fused_kernel<true>, ma, mb, p)
+                          : cudaLaunchKernelEx(&cfg, cov_i8_fused_kernel<false>, ma, mb, p);
+        }
+        if (le != cudaSuccess) return -(int)le;
+      }
       DCG_I8_STEP("fused");
     }
     if (timedf) cudaEventRecord(g_timing.c1[g_timing.n++], st);
