@@ -51,6 +51,8 @@ _SIGNATURES = {
                                  _p, _p, _p, _p, _c_int, _p, _p, _c_sz, _p]),
     "dcg_kmeans_update": (_c_int, [_p, _p, _c_int, _c_int, _p, _p, _p]),
     "dcg_kmeans_iterate": (_c_int, [_p, _c_i64, _c_int, _c_i64, _c_int, _p, _c_int, _p, _p, _p, _p, _c_sz, _p]),
+    "dcg_kmeans_iterate_n": (_c_int, [_p, _c_i64, _c_int, _c_i64, _c_int, _p, _c_int, _p, _p, _p, _c_int, C.c_double,
+                                      _p, _c_sz, _p]),
     "dcg_nearest_workspace_bytes": (_c_sz, [_c_i64, _c_int, _c_int]),
     "dcg_nearest_to_centers": (_c_int, [_p, _c_i64, _c_int, _c_i64, _c_int, _p, _c_int, _p,
                                         _p, _c_sz, _p]),

@@ -54,6 +54,7 @@ kmeans_step_kernel(const T* __restrict__ Y, int64_t n, int d, int64_t ld,
                    const double* __restrict__ centers, int k, int32_t* __restrict__ labels,
                    double* __restrict__ sums, double* __restrict__ counts, double* __restrict__ stats,
                    T* __restrict__ gap, int update_sums, const double* __restrict__ y_absmax, KmSmemPlan plan) {
+  if ((update_sums & 2) && stats[kKmCtlOffset] != 0.0) return;       // dcg_kmeans_iterate_n: the run has stopped
   constexpr int kKmR = km_frames_per_thread(DP);
   constexpr int kKmTile = kKmThreads * kKmR;
   extern __shared__ __align__(16) unsigned char smem[];
@@ -268,8 +269,14 @@ kmeans_step_kernel(const T* __restrict__ Y, int64_t n, int d, int64_t ld,
 // One CTA.  info[0] = number of empty clusters.  When there is none, the centres are updated in
 // place and info[1] = sum ||c_new - c_old||^2 (the Lloyd driver's convergence test); with empty
 // clusters nothing is touched: the driver relocates them first (rare path).
+// `ctl` (dcg_kmeans_iterate_n; null otherwise) = [stop, iterations done, tolerance]: a stopped run is left
+// untouched; otherwise the iteration is counted and the run stops when a cluster is empty, no label changed
+// (stats[0], three doubles before info) or the centre shift is within the tolerance -- the Lloyd driver's own
+// tests (statistics.py:159-197 of the reference, via scikit-learn), taken on the device.
 __global__ void kmeans_update_kernel(const double* __restrict__ sums, const double* __restrict__ counts,
-                                     int k, int d, double* __restrict__ centers, double* __restrict__ info) {
+                                     int k, int d, double* __restrict__ centers, double* __restrict__ info,
+                                     double* __restrict__ ctl) {
+  if (ctl && ctl[0] != 0.0) return;
   __shared__ int s_empty;
   __shared__ double s_shift[32];
   if (threadIdx.x == 0) s_empty = 0;
@@ -297,7 +304,18 @@ __global__ void kmeans_update_kernel(const double* __restrict__ sums, const doub
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_shift[w];
     info[0] = (double)n_empty;
     info[1] = t;
+    if (ctl) {
+      ctl[1] += 1.0;
+      if (n_empty > 0 || info[-3] == 0.0 || t <= ctl[2]) ctl[0] = 1.0;
+    }
   }
+}
+
+// zero `n` doubles unless the run has stopped; a fresh run (init) also resets ctl = [0, 0, tol]
+__global__ void kmeans_zero_kernel(double* __restrict__ p, int n, double* __restrict__ ctl, int init, double tol) {
+  if (init && blockIdx.x == 0 && threadIdx.x == 0) { ctl[0] = 0.0; ctl[1] = 0.0; ctl[2] = tol; }
+  if (!init && ctl[0] != 0.0) return;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = 0.0;
 }
 
 // ---- K3 ----------------------------------------------------------------------------------------
@@ -408,7 +426,9 @@ extern "C" int dcg_kmeans_step(const void* Y, int64_t n, int d, int64_t ld, int 
   if (n <= 0 || d < 1 || d > 32 || ld < d || k < 1) return DCG_E_SHAPE;
   if (dtype_bytes != 4 && dtype_bytes != 8) return DCG_E_MODE;
   cudaStream_t st = (cudaStream_t)stream;
-  if (update_sums && counts == sums + (size_t)k * d && stats == counts + k) {
+  if (update_sums & 2) {
+    // dcg_kmeans_iterate_n zeroes the buffer itself (conditionally: a stopped run keeps its last result)
+  } else if (update_sums && counts == sums + (size_t)k * d && stats == counts + k) {
     // [sums | counts | stats] in one buffer (dcg_kmeans_iterate): one memset
     DCG_CUDA_TRY(cudaMemsetAsync(sums, 0, ((size_t)k * d + k + 3) * sizeof(double), st));
   } else {
@@ -438,7 +458,7 @@ extern "C" int dcg_kmeans_update(const double* sums, const double* counts, int k
                                  double* centers, double* info, void* stream) {
   if (!sums || !counts || !centers || !info) return DCG_E_NULL;
   if (k < 1 || d < 1 || d > 32) return DCG_E_SHAPE;
-  kmeans_update_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(sums, counts, k, d, centers, info);
+  kmeans_update_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(sums, counts, k, d, centers, info, nullptr);
   DCG_LAUNCH_CHECK();
   return 0;
 }
@@ -455,6 +475,32 @@ extern "C" int dcg_kmeans_iterate(const void* Y, int64_t n, int d, int64_t ld, i
                                  1, y_absmax, ws, ws_bytes, stream);
   if (rc) return rc;
   return dcg_kmeans_update(sums, counts, k, d, centers, info, stream);
+}
+
+extern "C" int dcg_kmeans_iterate_n(const void* Y, int64_t n, int d, int64_t ld, int dtype_bytes,
+                                    double* centers, int k, int32_t* labels, double* work,
+                                    const double* y_absmax, int iters, double tol,
+                                    void* ws, size_t ws_bytes, void* stream) {
+  if (!work) return DCG_E_NULL;
+  if (iters < 1 || k < 1 || d < 1) return DCG_E_SHAPE;
+  double* sums = work;
+  double* counts = work + (size_t)k * d;
+  double* stats = counts + k;
+  double* info = stats + 3;
+  double* ctl = stats + kKmCtlOffset;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nz = k * d + k + 3;
+  const int zb = std::min(64, (nz + 255) / 256);
+  for (int it = 0; it < iters; ++it) {
+    kmeans_zero_kernel<<<zb, 256, 0, st>>>(sums, nz, ctl, it == 0, tol);
+    DCG_LAUNCH_CHECK();
+    const int rc = dcg_kmeans_step(Y, n, d, ld, dtype_bytes, centers, k, labels, sums, counts, stats, nullptr,
+                                   3, y_absmax, ws, ws_bytes, stream);
+    if (rc) return rc;
+    kmeans_update_kernel<<<1, 512, 0, st>>>(sums, counts, k, d, centers, info, ctl);
+    DCG_LAUNCH_CHECK();
+  }
+  return 0;
 }
 
 extern "C" size_t dcg_nearest_workspace_bytes(int64_t n, int d, int k) {

@@ -4,6 +4,11 @@
 
 namespace dcg {
 
+// dcg_kmeans_iterate_n: the run's control words [stop, iterations done, tolerance] sit this many doubles
+// after `stats` in the work buffer ([sums | counts | stats 3 | info 2 | ctl 3]); a kernel launched with bit 1
+// of `update_sums` set returns at once when stop != 0.
+constexpr int kKmCtlOffset = 5;
+
 // FP64 re-evaluation of one frame over all centres (rare path), by the whole warp: the frame is
 // broadcast through shared memory, lane l scores centres l, l + 32, ..., and the partial
 // (best, second, label) triples are merged by shuffles with the lowest-index tie-break.  All lanes

@@ -89,6 +89,7 @@ kmeans_mma_kernel(const T* __restrict__ Y, int64_t n, int d, int64_t ld,
                   const double* __restrict__ centers, int k, int32_t* __restrict__ labels,
                   double* __restrict__ sums, double* __restrict__ counts, double* __restrict__ stats,
                   T* __restrict__ gap, int update_sums, const double* __restrict__ y_absmax, Plan plan) {
+  if ((update_sums & 2) && stats[kKmCtlOffset] != 0.0) return;       // dcg_kmeans_iterate_n: the run has stopped
   extern __shared__ __align__(128) unsigned char smem[];
   uint4* b_s = reinterpret_cast<uint4*>(smem);                         // [n-tile of 8 centres][lane] -> bhi0 bhi1 blo0 blo1
   double* yy_s = reinterpret_cast<double*>(smem + plan.yy_off);

@@ -60,44 +60,48 @@ def _shift_invert_topk(B: torch.Tensor, Ct: torch.Tensor, out: int, tol: float =
     eye = torch.eye(F, dtype=B.dtype, device=B.device)
     eye_b = torch.eye(b, dtype=B.dtype, device=B.device)
 
-    def factor(sig):
-        """sig: (nb, 1, 1).  Returns (K, Lk^-1) or None if any K is not positive definite."""
+    def factor(sig, check=True):
+        """sig: (nb, 1, 1).  Returns (K, K^-1, K^-1 B, info) or None if any K is not positive definite.
+        ``check=False`` skips the host read of the factorisation status (the caller reads ``info`` later,
+        together with the residuals: a failed factor shows there before any result is accepted)."""
         Kmat = sig * B - Ct
         Lk, info = torch.linalg.cholesky_ex(Kmat)
-        if int(info.abs().max().item()) != 0:
+        if check and int(info.abs().max().item()) != 0:
             return None
-        return Kmat, torch.linalg.solve_triangular(Lk, eye.expand(nb, F, F), upper=False)
+        Li = torch.linalg.solve_triangular(Lk, eye.expand(nb, F, F), upper=False)
+        Kinv = Li.mT @ Li                       # two F^3 products (70 us each at F = 1000) buy 1 instead of 6
+        return Kmat, Kinv, Kinv @ B, info       # skinny products per cheap step, 4 per accurate one
 
     sigma = torch.full((nb, 1, 1), 1.05, dtype=B.dtype, device=B.device)
-    fac = None
-    for _ in range(3):
-        fac = factor(sigma)
-        if fac is not None:
-            break
-        sigma = sigma * 2.0
-    if fac is None:
-        return None
+    # the first factorisation is used unchecked: its status rides on the first round's host read
+    fac = factor(sigma, check=False)
+    pending_info = fac[3]
+
+    def step_cheap(Xc):
+        """X <- (K^-1 B) X with the explicitly formed operator: one product.  Its rounding (eps cond(K)) perturbs
+        the operator, not the convergence: used for the first steps only, the accurate steps that follow
+        converge to the eigenvectors of the true pencil."""
+        return fac[2] @ Xc
 
     def solve(Z):
-        Kmat, Li = fac
-        Y = Li.mT @ (Li @ Z)
-        # one step of iterative refinement.  (K^-1 formed explicitly as Li^T Li halves the GEMM count
-        # but costs accuracy: measured 12 iterations instead of 8 to reach the 1e-12 residual.)
-        return torch.baddbmm(Y, Li.mT, Li @ torch.baddbmm(Z, Kmat, Y, alpha=-1.0))
+        Kmat, Kinv = fac[0], fac[1]
+        Y = Kinv @ Z
+        # one step of iterative refinement against K itself
+        return torch.baddbmm(Y, Kinv, torch.baddbmm(Z, Kmat, Y, alpha=-1.0))
 
     X = _start_block(F, b, B.device).expand(nb, F, b)
     it = 0
     reshifted = False
     for rnd in range(max_rounds):
-        # the first Rayleigh-Ritz after 8 steps (4 are rarely enough for 1e-12, and a Ritz step with
-        # its small eigh and host read costs as much as 4 iterations); columns are rescaled every
+        # the first Rayleigh-Ritz after 12 steps (8 are rarely enough for 1e-12, and a Ritz step with its
+        # small eigen-solve, residual and host read costs as much as 4 iterations); columns are rescaled every
         # other step (the iteration amplifies by at most 1 / (sigma - lambda_max) per step)
-        for i in range(8 if rnd == 0 else 4):
-            X = solve(B @ X)
+        for i in range(12 if rnd == 0 else 4):
+            X = step_cheap(X) if (rnd == 0 and i < 8) else solve(B @ X)
             if i & 1:
                 X = X / torch.linalg.norm(X, dim=-2, keepdim=True)
-            if i == 3 and rnd == 0:
-                # re-orthogonalise half way (Cholesky QR, no host read): the noise directions shrink by
+            if i & 3 == 3 and rnd == 0 and i < 11:
+                # re-orthogonalise every 4 steps (Cholesky QR, no host read): the noise directions shrink by
                 # (sigma - lambda_max) / sigma per step, so after 8 plain steps the block would be
                 # numerically rank deficient
                 G = X.mT @ X
@@ -127,8 +131,26 @@ def _shift_invert_topk(B: torch.Tensor, Ct: torch.Tensor, out: int, tol: float =
         rel = res / (nrm * torch.linalg.norm(X[..., :out], dim=-2))
         # one host read per round: worst residual + the Ritz values the shift logic needs
         host = torch.cat([rel.max().reshape(1), theta[:, 0], theta[:, out - 1], theta[:, b - 1],
-                          sigma.reshape(-1), bad.max().reshape(1)]).tolist()
+                          sigma.reshape(-1), bad.max().reshape(1),
+                          pending_info.abs().max().to(B.dtype).reshape(1)]).tolist()
         if host[-1] != 0:
+            # sigma = 1.05 was not above the spectrum: checked factorisations with larger shifts, start over
+            if rnd > 0:
+                return None
+            fac = None
+            for _ in range(2):
+                sigma = sigma * 2.0
+                fac = factor(sigma)
+                if fac is not None:
+                    break
+            if fac is None:
+                return None
+            pending_info = torch.zeros_like(pending_info)
+            X = _start_block(F, b, B.device).expand(nb, F, b)
+            it = 0
+            reshifted = True                   # no second re-shift on this path
+            continue
+        if host[-2] != 0 or host[0] != host[0]:
             return None
         worst = host[0]
         if worst <= tol:

@@ -81,6 +81,10 @@ def _kmeanspp_sklearn(Yc: torch.Tensor, k: int, rs: np.random.RandomState) -> to
     return centers
 
 
+# Lloyd iterations enqueued per host read on one device (dcg_kmeans_iterate_n)
+_LLOYD_BATCH = 4
+
+
 def kmeans_lloyd(Y: torch.Tensor, init_centers: torch.Tensor, max_iter: int = 300, tol: float = 1e-4,
                  shards: Optional[FrameShards] = None, want_gap: bool = False) -> Dict:
     """Lloyd iterations on the device; ``Y`` is this rank's (frames x d) shard (float32/64),
@@ -117,12 +121,16 @@ def kmeans_lloyd(Y: torch.Tensor, init_centers: torch.Tensor, max_iter: int = 30
     res = None
     C = C.contiguous()
     work = ops.kmeans_work(k, d, dev)
-    for it in range(max_iter):
+    it = 0
+    while it < max_iter:
         if shards is None:
-            # single device: memset + E-step + FP64 sums + M-step finish in one library call
-            res = ops.kmeans_iterate_(Yc, C, labels, work, absmax=absmax)
+            # single device: up to _LLOYD_BATCH whole iterations (zero + E-step + FP64 sums + M-step finish each)
+            # per library call; the convergence tests run on the device and the launches after the stopping
+            # iteration are no-ops, so the state is the one a one-at-a-time loop would have stopped in
+            res = ops.kmeans_iterate_n_(Yc, C, labels, work, min(_LLOYD_BATCH, max_iter - it), tol_eff, absmax=absmax)
             sums, counts = res["sums"], res["counts"]
-            changed, _, _, n_empty, shift_tot = work[k * d + k:k * d + k + 5].tolist()   # ONE host read
+            changed, _, _, n_empty, shift_tot, _, done, _ = work[k * d + k:k * d + k + 8].tolist()   # ONE host read
+            it += int(done)
         else:
             # [sums | counts | stats] land in one buffer and are all-reduced in place
             res = ops.kmeans_step_packed_(Yc, C, labels, work, absmax=absmax)
@@ -132,6 +140,7 @@ def kmeans_lloyd(Y: torch.Tensor, init_centers: torch.Tensor, max_iter: int = 30
             # ONE host read per iteration: [changed, inertia, ties, n_empty, shift]
             ops.kmeans_update_(C, sums, counts, info=work[k * d + k + 3:k * d + k + 5])
             changed, _, _, n_empty, shift_tot = work[k * d + k:k * d + k + 5].tolist()
+            it += 1
         if n_empty > 0:
             empty = torch.nonzero(counts == 0).flatten()
             sums, counts = _relocate_empty(Yc, C, labels, sums, counts, empty, shards)
@@ -140,7 +149,7 @@ def kmeans_lloyd(Y: torch.Tensor, init_centers: torch.Tensor, max_iter: int = 30
             C_new[nz] = sums[nz] * (1.0 / counts[nz]).unsqueeze(1)
             shift_tot = float(((C_new - C) ** 2).sum().item())
             C = C_new
-        n_iter = it + 1
+        n_iter = it
         if changed == 0:
             strict = True
             break

@@ -390,8 +390,35 @@ def kmeans_update_(centers: torch.Tensor, sums: torch.Tensor, counts: torch.Tens
 
 
 def kmeans_work(k: int, d: int, device) -> torch.Tensor:
-    """Work buffer of ``kmeans_iterate_``: [sums k*d | counts k | stats 3 | info 2] FP64."""
-    return torch.empty(k * d + k + 5, dtype=torch.float64, device=device)
+    """Work buffer of ``kmeans_iterate_`` / ``kmeans_iterate_n_``:
+    [sums k*d | counts k | stats 3 | info 2 | ctl 3] FP64."""
+    return torch.empty(k * d + k + 8, dtype=torch.float64, device=device)
+
+
+def kmeans_iterate_n_(Y: torch.Tensor, centers: torch.Tensor, labels: torch.Tensor, work: torch.Tensor,
+                      iters: int, tol: float, absmax: Optional[torch.Tensor] = None) -> dict:
+    """Up to ``iters`` Lloyd iterations in ONE library call and without a host round trip: the convergence
+    tests (no label changed / centre shift <= ``tol`` / a cluster came out empty) run on the device and the
+    launches after the stopping iteration return at once.  Returns views into ``work`` as ``kmeans_iterate_``
+    plus ``ctl`` = [stopped, iterations done, tol]."""
+    _need_cuda("Y", Y)
+    _need_cuda("centers", centers, torch.float64)
+    _need_cuda("labels", labels, torch.int32)
+    _need_cuda("work", work, torch.float64)
+    n, d, ld = _rows("Y", Y)
+    k = centers.shape[0]
+    if not centers.is_contiguous() or centers.shape[1] != d or work.numel() < k * d + k + 8:
+        raise ValueError("centers must be contiguous (k, d) and work at least k*d + k + 8 doubles")
+    ws = _KM_WS.get(Y.device)
+    if ws is None:
+        ws = _KM_WS[Y.device] = _ws(256, Y.device)
+    _call(Y.device, "dcg_kmeans_iterate_n", Y.data_ptr(), n, d, ld, _dtype_bytes(Y), centers.data_ptr(), k,
+              labels.data_ptr(), work.data_ptr(), _absmax_ptr(absmax, Y.device), int(iters), float(tol),
+              ws.data_ptr(), ws.numel(), _stream(Y.device))
+    _count(3 * int(iters))
+    o = k * d
+    return {"sums": work[:o].view(k, d), "counts": work[o:o + k], "stats": work[o + k:o + k + 3],
+            "info": work[o + k + 3:o + k + 5], "ctl": work[o + k + 5:o + k + 8]}
 
 
 def kmeans_iterate_(Y: torch.Tensor, centers: torch.Tensor, labels: torch.Tensor,

@@ -189,6 +189,18 @@ int dcg_kmeans_iterate(const void* Y, int64_t n, int d, int64_t ld, int dtype_by
                        double* centers, int k, int32_t* labels, double* work,
                        const double* y_absmax, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- K1: up to `iters` Lloyd iterations on one device without a host round trip -------------------
+ * The Lloyd driver of statistics.kmeans_clustering (reference statistics.py:159-197, scikit-learn's
+ * lloyd loop) reads (changed, empty, shift) after every iteration.  Here the tests run on the device:
+ * `work` holds k*d + k + 8 doubles [sums | counts | stats 3 | info 2 | ctl 3]; ctl = [stop, done, tol].
+ * The iterations are all enqueued; after the one in which a cluster came out empty, no label changed or
+ * the centre shift is <= tol, the remaining launches return at once, so `work`, `centers` and `labels`
+ * hold exactly the state dcg_kmeans_iterate would have left at that iteration and ctl[1] says which.  */
+int dcg_kmeans_iterate_n(const void* Y, int64_t n, int d, int64_t ld, int dtype_bytes,
+                         double* centers, int k, int32_t* labels, double* work,
+                         const double* y_absmax, int iters, double tol,
+                         void* ws, size_t ws_bytes, void* stream);
+
 /* ---- K3: nearest sample to each centre -------------------------------------------------------
  * Replaces `statistics.find_centroids` (statistics.py:370-377): argmin_t ||y_t - c_j||_2 per
  * centre j, first index on ties, evaluated in FP64.  argmin is int64[k].                        */

@@ -661,6 +661,41 @@ def test_kmeans_small_k_sums_with_private_accumulators(dev, k, d):
     np.testing.assert_array_equal(res["counts"].cpu().numpy(), np.bincount(got, minlength=k))
 
 
+@pytest.mark.parametrize("k,d,n,tol", [(7, 3, 40_000, 0.0), (100, 4, 200_000, 0.5), (1000, 10, 60_000, 1e-3)])
+def test_kmeans_batched_iterations_stop_where_the_one_at_a_time_loop_stops(dev, k, d, n, tol):
+    """dcg_kmeans_iterate_n enqueues several Lloyd iterations and takes the driver's convergence tests on the
+    device: labels, centres, sums and the iteration count must be those of a loop of dcg_kmeans_iterate with a
+    host read after every iteration (reference statistics.py:159-197 via scikit-learn's lloyd loop)."""
+    from deep_cartograph_b200 import ops
+    rng = np.random.default_rng(k)
+    cent = rng.normal(size=(k, d)) * 4
+    Y = _cuda((cent[rng.integers(0, k, size=n)] + rng.normal(size=(n, d))).astype(np.float32), dev)
+    C0 = Y[:k].to(torch.float64).clone()
+    absmax = Y.abs().amax().to(torch.float64).reshape(1)
+    o = k * d + k
+    # one at a time
+    C1, lab1, w1 = C0.clone(), torch.full((n,), -1, dtype=torch.int32, device=dev), ops.kmeans_work(k, d, dev)
+    n1 = 0
+    for it in range(40):
+        ops.kmeans_iterate_(Y, C1, lab1, w1, absmax=absmax)
+        changed, _, _, n_empty, shift = w1[o:o + 5].tolist()
+        n1 = it + 1
+        if n_empty > 0 or changed == 0 or shift <= tol:
+            break
+    # batches of 7
+    C2, lab2, w2 = C0.clone(), torch.full((n,), -1, dtype=torch.int32, device=dev), ops.kmeans_work(k, d, dev)
+    n2 = 0
+    while n2 < 40:
+        r = ops.kmeans_iterate_n_(Y, C2, lab2, w2, min(7, 40 - n2), tol, absmax=absmax)
+        stopped, done, _ = r["ctl"].tolist()
+        n2 += int(done)
+        if stopped:
+            break
+    assert n1 == n2, (n1, n2)
+    assert torch.equal(lab1, lab2) and torch.equal(C1, C2)
+    assert torch.equal(w1[:o + 5], w2[:o + 5])
+
+
 def test_kmeans_empty_cluster_relocation(dev):
     from deep_cartograph_b200.modules.statistics import statistics
     X = np.array([[0.0, 0.0], [0.1, 0.0], [5.0, 5.0], [5.1, 5.0], [9.0, 9.0]])

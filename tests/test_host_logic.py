@@ -409,10 +409,26 @@ def test_lloyd_driver_control_flow_with_emulated_kernel(monkeypatch, kmeans_ref)
         return {"sums": work[:k * d].view(k, d), "counts": work[k * d:k * d + k],
                 "stats": work[k * d + k:k * d + k + 3], "info": work[k * d + k + 3:k * d + k + 5]}
 
+    def fake_iterate_n(Y, C, labels, work, iters, tol, absmax=None):
+        # dcg_kmeans_iterate_n: up to `iters` iterations, the convergence tests taken "on the device";
+        # work = [sums | counts | stats 3 | info 2 | ctl 3], ctl = [stopped, iterations done, tol]
+        k, d = C.shape
+        o = k * d + k
+        work[o + 5:o + 8] = torch.tensor([0.0, 0.0, tol], dtype=torch.float64)
+        r = None
+        for _ in range(iters):
+            r = fake_iterate(Y, C, labels, work)
+            work[o + 6] += 1.0
+            if float(work[o + 3]) > 0 or float(work[o]) == 0.0 or float(work[o + 4]) <= tol:
+                work[o + 5] = 1.0
+                break
+        return dict(r, ctl=work[o + 5:o + 8])
+
     monkeypatch.setattr(ops, "kmeans_step", fake_step)
     monkeypatch.setattr(ops, "kmeans_update_", fake_update)
     monkeypatch.setattr(ops, "kmeans_iterate_", fake_iterate)
-    monkeypatch.setattr(ops, "kmeans_work", lambda k, d, device: torch.zeros(k * d + k + 5, dtype=torch.float64))
+    monkeypatch.setattr(ops, "kmeans_iterate_n_", fake_iterate_n)
+    monkeypatch.setattr(ops, "kmeans_work", lambda k, d, device: torch.zeros(k * d + k + 8, dtype=torch.float64))
     for name in ("blobs_d2_k5", "blobs_d4_k10_grid", "uniform_d3_k7_grid"):
         X = torch.from_numpy(kmeans_ref[f"{name}_X"])
         res = statistics.kmeans_lloyd(X, torch.from_numpy(kmeans_ref[f"{name}_init"]))

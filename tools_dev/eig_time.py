@@ -40,3 +40,7 @@ for name, fn in [("cholesky_ex", lambda: torch.linalg.cholesky_ex(B)),
                  ("trsm small", lambda: torch.linalg.solve_triangular(torch.linalg.cholesky(Xb.T @ Xb + torch.eye(12, dtype=torch.float64, device=dev)), Xb, upper=False, left=False)),
                  ("eigh F", lambda: torch.linalg.eigh(B))]:
     print(f"  {name:16s} {timeit(fn)[0]:.3f} ms")
+Bm = torch.randn(F, F, dtype=torch.float64, device=dev)
+print(f"  {'F^3 GEMM':16s} {timeit(lambda: Bm @ B)[0]:.3f} ms")
+print(f"  {'trsm inverse':16s} {timeit(lambda: torch.linalg.solve_triangular(L, torch.eye(F, dtype=torch.float64, device=dev), upper=False))[0]:.3f} ms")
+print(f"  {'cholesky_inverse':16s} {timeit(lambda: torch.cholesky_inverse(L))[0]:.3f} ms")
