@@ -95,10 +95,13 @@ def main():
         ref = f64.lagged_sums(X, lag, mean, rng)
         scale = ref["S0"].abs().max()
         assert sums["M"] == s1["M"] == ref["M"] == n - lag
+        # (the exact integer engine returns the SYMMETRIC part of St -- all that TICA uses, mlcolvar symmetrises
+        #  C_tau -- so St is compared through its symmetric part whatever the engine)
+        sym = lambda t: 0.5 * (t + t.T)
         for key in ("S0", "St"):
-            assert ((sums[key] - s1[key]).abs().max() / scale).item() < 4e-6, key
-            assert ((sums[key] - ref[key]).abs().max() / scale).item() < 1e-5, key
-            assert ((s1[key] - ref[key]).abs().max() / scale).item() < 1e-5, key
+            assert ((sym(sums[key]) - sym(s1[key])).abs().max() / scale).item() < 4e-6, key
+            assert ((sym(sums[key]) - sym(ref[key])).abs().max() / scale).item() < 1e-5, key
+            assert ((sym(s1[key]) - sym(ref[key])).abs().max() / scale).item() < 1e-5, key
         for key in ("a", "b"):
             assert (sums[key] - ref[key]).abs().max().item() < 1e-6 * n, key
         # (3) TICA
