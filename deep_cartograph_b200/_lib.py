@@ -30,6 +30,8 @@ _SIGNATURES = {
     "dcg_device_info": (_c_int, [C.POINTER(_c_int)] * 3),
     "dcg_colstats_workspace_bytes": (_c_sz, [_c_i64, _c_int]),
     "dcg_colstats_f32": (_c_int, [_p, _c_i64, _c_int, _c_i64, _p, _p, _p, _p, _p, _c_sz, _p]),
+    "dcg_stats_pack": (_c_int, [C.c_double, _p, _p, _p, _p, _c_int, _p, _p]),
+    "dcg_stats_merge": (_c_int, [_p, _c_int, _c_int, _p, _p, _p, _p, _p, _p]),
     "dcg_standardize_f32": (_c_int, [_p, _c_i64, _c_int, _c_i64, _p, _p, _p]),
     "dcg_gather_standardize_f32": (_c_int, [_p, _c_i64, _c_int, _c_i64, _p, _c_i64, _c_i64, _p, _p, _p, _p]),
     "dcg_cov_workspace_bytes": (_c_sz, [_c_i64, _c_int, _c_int, _c_int, _c_int]),

@@ -256,3 +256,67 @@ extern "C" int dcg_colstats_f32(const float* X, int64_t n, int f, int64_t ld,
   DCG_LAUNCH_CHECK();
   return 0;
 }
+
+
+// ---- statistics of frame shards ------------------------------------------------------------
+// pack: [n | mean f | m2 f | min f | max f] as doubles, the record every rank contributes to the all-gather
+__global__ void stats_pack_kernel(double n, const double* __restrict__ mean, const double* __restrict__ m2,
+                                  const float* __restrict__ mn, const float* __restrict__ mx, int f,
+                                  double* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j == 0) out[0] = n;
+  if (j >= f) return;
+  out[1 + j] = mean[j];
+  out[1 + f + j] = m2[j];
+  out[1 + 2 * f + j] = (double)mn[j];
+  out[1 + 3 * f + j] = (double)mx[j];
+}
+
+// merge of `world` packed records (Chan et al., FP64): N = sum n_r, mean = sum n_r mean_r / N,
+// M2 = sum M2_r + sum n_r (mean_r - mean)^2, min / max over the ranks that hold frames.
+__global__ void stats_merge_kernel(const double* __restrict__ all, int world, int f,
+                                   double* __restrict__ mean, double* __restrict__ m2,
+                                   float* __restrict__ mn, float* __restrict__ mx, double* __restrict__ n_out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= f) return;
+  const size_t rec = 1 + 4 * (size_t)f;
+  double N = 0.0, s = 0.0;
+  for (int r = 0; r < world; ++r) {
+    const double n = all[r * rec];
+    if (n > 0.0) { N += n; s += n * all[r * rec + 1 + j]; }
+  }
+  const double mu = s / N;
+  double q = 0.0, lo = INFINITY, hi = -INFINITY;
+  for (int r = 0; r < world; ++r) {
+    const double n = all[r * rec];
+    if (!(n > 0.0)) continue;
+    const double d = all[r * rec + 1 + j] - mu;
+    q += all[r * rec + 1 + f + j] + n * d * d;
+    lo = fmin(lo, all[r * rec + 1 + 2 * f + j]);
+    hi = fmax(hi, all[r * rec + 1 + 3 * f + j]);
+  }
+  mean[j] = mu;
+  m2[j] = q;
+  mn[j] = (float)lo;
+  mx[j] = (float)hi;
+  if (j == 0 && n_out) *n_out = N;
+}
+
+extern "C" int dcg_stats_pack(double n, const double* mean, const double* m2, const float* minv, const float* maxv,
+                              int f, double* packed, void* stream) {
+  if (!mean || !m2 || !minv || !maxv || !packed) return DCG_E_NULL;
+  if (f <= 0 || n < 0) return DCG_E_SHAPE;
+  stats_pack_kernel<<<(unsigned)dcg::ceil_div(f, 256), 256, 0, (cudaStream_t)stream>>>(n, mean, m2, minv, maxv, f, packed);
+  DCG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dcg_stats_merge(const double* all_packed, int world, int f, double* mean, double* m2,
+                               float* minv, float* maxv, double* n_total, void* stream) {
+  if (!all_packed || !mean || !m2 || !minv || !maxv) return DCG_E_NULL;
+  if (f <= 0 || world <= 0) return DCG_E_SHAPE;
+  stats_merge_kernel<<<(unsigned)dcg::ceil_div(f, 128), 128, 0, (cudaStream_t)stream>>>(all_packed, world, f, mean, m2, minv,
+                                                                                        maxv, n_total);
+  DCG_LAUNCH_CHECK();
+  return 0;
+}

@@ -148,6 +148,37 @@ def standardize_(X: torch.Tensor, mean: torch.Tensor, rng: torch.Tensor) -> torc
     return X
 
 
+def stats_pack(st: dict) -> torch.Tensor:
+    """This rank's column statistics as one FP64 record [n | mean | m2 | min | max] (one launch): the
+    contribution to the all-gather of ``FrameShards.merge_stats``."""
+    mean, m2, mn, mx = st["mean"], st["m2"], st["min"], st["max"]
+    _need_cuda("mean", mean, torch.float64)
+    f = mean.numel()
+    out = torch.empty(1 + 4 * f, dtype=torch.float64, device=mean.device)
+    _call(mean.device, "dcg_stats_pack", float(st["n"]), mean.contiguous().data_ptr(), m2.contiguous().data_ptr(),
+          mn.contiguous().data_ptr(), mx.contiguous().data_ptr(), f, out.data_ptr(), _stream(mean.device))
+    _count(1)
+    return out
+
+
+def stats_merge(all_packed: torch.Tensor, world: int, f: int) -> dict:
+    """Chan merge of ``world`` packed records (one launch, FP64).  Returns dict(mean, m2, min, max, n) with
+    ``n`` a 1-element FP64 device tensor (no host read here)."""
+    _need_cuda("all_packed", all_packed, torch.float64)
+    if all_packed.numel() != world * (1 + 4 * f):
+        raise ValueError("all_packed must hold world records of 1 + 4 f doubles")
+    dev = all_packed.device
+    mean = torch.empty(f, dtype=torch.float64, device=dev)
+    m2 = torch.empty(f, dtype=torch.float64, device=dev)
+    mn = torch.empty(f, dtype=torch.float32, device=dev)
+    mx = torch.empty(f, dtype=torch.float32, device=dev)
+    n = torch.empty(1, dtype=torch.float64, device=dev)
+    _call(dev, "dcg_stats_merge", all_packed.contiguous().data_ptr(), world, f, mean.data_ptr(), m2.data_ptr(),
+          mn.data_ptr(), mx.data_ptr(), n.data_ptr(), _stream(dev))
+    _count(1)
+    return {"mean": mean, "m2": m2, "min": mn, "max": mx, "n": n}
+
+
 # ---- A5/A6/A7/A8 ------------------------------------------------------------------------------
 def lagged_covariance(X: torch.Tensor, lag: int, mean: Optional[torch.Tensor] = None,
                       rng: Optional[torch.Tensor] = None, block: int = 0, engine=None,

@@ -42,6 +42,16 @@ class FrameShards:
         the caller already knows ``n_total`` (repeated passes over the same shards)."""
         f = st["mean"].numel()
         dev = st["mean"].device
+        if dev.type == "cuda":
+            # one launch to pack, one collective, one launch to merge (the eager version below is ~25 small
+            # kernels: 0.25 ms of the C2 step at every GPU count > 1)
+            from . import ops
+            packed = ops.stats_pack(st)
+            flat = torch.empty(self.world * (1 + 4 * f), dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(flat, packed, group=self.group)
+            m = ops.stats_merge(flat, self.world, f)
+            n_all = int(n_total) if n_total is not None else int(round(float(m["n"].item())))
+            return {"n": n_all, "mean": m["mean"], "m2": m["m2"], "min": m["min"], "max": m["max"]}
         packed = torch.empty(1 + 4 * f, dtype=torch.float64, device=dev)
         packed[0] = float(st["n"])
         packed[1:1 + f] = st["mean"]

@@ -59,6 +59,16 @@ int dcg_colstats_f32(const float* X, int64_t n, int f, int64_t ld,
                      double* mean, double* m2, float* minv, float* maxv,
                      void* ws, size_t ws_bytes, void* stream);
 
+/* ---- A2 across frame shards --------------------------------------------------------
+ * The reference computes the statistics over the concatenated trajectories (cv_calculator.py:295-297);
+ * with the frames sharded over GPUs every rank contributes one packed record
+ * [n | mean f | m2 f | min f | max f] (doubles) to ONE all-gather, and dcg_stats_merge combines the
+ * `world` records (Chan's parallel update, FP64; ranks with n = 0 are skipped).  n_total may be NULL. */
+int dcg_stats_pack(double n, const double* mean, const double* m2, const float* minv, const float* maxv,
+                   int f, double* packed, void* stream);
+int dcg_stats_merge(const double* all_packed, int world, int f, double* mean, double* m2,
+                    float* minv, float* maxv, double* n_total, void* stream);
+
 /* ---- A4: in-place standardisation ------------------------------------------------------------
  * Replaces `LinearCalculator.normalize_data` (cv_calculator.py:806-837): x = (x - mean[j]) /
  * range[j] with IEEE float32 subtraction and division.  Also used for the CV normalisation of

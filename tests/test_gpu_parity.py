@@ -67,6 +67,35 @@ def test_colstats_strided_rows_and_golden(dev, c1):
 # ------------------------------------------------------------------------------------------------
 # A4 standardisation (bit-exact IEEE sub + div)
 # ------------------------------------------------------------------------------------------------
+def test_sharded_statistics_pack_and_merge_kernels(dev):
+    """dcg_stats_pack / dcg_stats_merge (the two launches around the statistics all-gather of the frame-sharded
+    path): shards of unequal length, one of them EMPTY, merged == the statistics of the whole matrix."""
+    from deep_cartograph_b200 import ops
+    n, f = 50_001, 333
+    X = synth_features(n, f, seed=9)
+    Xd = _cuda(X, dev)
+    cuts = [0, 17_000, 17_000, 40_001, n]                  # the second shard is empty
+    recs = []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        if b > a:
+            st = ops.column_stats(Xd[a:b])
+        else:
+            z64, z32 = torch.zeros(f, dtype=torch.float64, device=dev), torch.zeros(f, dtype=torch.float32, device=dev)
+            st = {"n": 0, "mean": z64, "m2": z64.clone(), "min": z32, "max": z32.clone()}
+        recs.append(ops.stats_pack(st))
+        assert recs[-1].numel() == 1 + 4 * f and float(recs[-1][0]) == b - a
+    m = ops.stats_merge(torch.cat(recs), len(recs), f)
+    whole = oracle.column_stats(X)
+    assert float(m["n"].item()) == n
+    np.testing.assert_allclose(m["mean"].cpu().numpy(), whole["mean"], rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(np.sqrt(m["m2"].cpu().numpy() / (n - 1)), whole["std"], rtol=2e-6)
+    one = ops.column_stats(Xd)                             # and == the single-launch statistics to FP64 rounding
+    np.testing.assert_allclose(m["mean"].cpu().numpy(), one["mean"].cpu().numpy(), rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(m["m2"].cpu().numpy(), one["m2"].cpu().numpy(), rtol=1e-7)
+    np.testing.assert_array_equal(m["min"].cpu().numpy(), whole["min"].astype(np.float32))
+    np.testing.assert_array_equal(m["max"].cpu().numpy(), whole["max"].astype(np.float32))
+
+
 @pytest.mark.parametrize("n,f", [(164, 54), (4096, 1000), (1000, 4950 // 5), (513, 7), (10000, 4), (33, 2)])
 def test_standardize_is_bit_exact(dev, n, f):
     from deep_cartograph_b200 import ops
