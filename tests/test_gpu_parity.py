@@ -721,8 +721,12 @@ def test_kmeans_batched_iterations_stop_where_the_one_at_a_time_loop_stops(dev, 
         if stopped:
             break
     assert n1 == n2, (n1, n2)
-    assert torch.equal(lab1, lab2) and torch.equal(C1, C2)
-    assert torch.equal(w1[:o + 5], w2[:o + 5])
+    # labels, counts and the integer statistics are identical; sums / centres / inertia / shift agree to the
+    # rounding of the cross-CTA FP64 adds (their order is not fixed)
+    assert torch.equal(lab1, lab2)
+    assert torch.equal(w1[k * d:o], w2[k * d:o]) and w1[o].item() == w2[o].item() and w1[o + 2].item() == w2[o + 2].item()
+    torch.testing.assert_close(C1, C2, rtol=1e-12, atol=1e-12)
+    torch.testing.assert_close(w1[:o + 5], w2[:o + 5], rtol=1e-10, atol=1e-10)
 
 
 def test_kmeans_empty_cluster_relocation(dev):
