@@ -228,6 +228,8 @@ def test_cov_unaligned_rows_and_block_origins(dev, f, ld_pad, block):
     (12000, 2000, 10, 0, 0, True),         # 136 tiles: two rounds of the persistent kernel
     (6000, 4950, 10, 495, 2, True),        # the C3 level-1 plan: 100 tiles, rounds that quantise feature sub-ranges
     (3001, 1000, 3, 0, 0, False),          # raw features (mode None), a last window that is partly empty
+    (200, 1000, 10, 0, 0, True),           # fewer frames than one window: a single, mostly empty one
+    (2500, 640, 128, 0, 0, True),          # a lag longer than a quantiser item (32 frames) and than a stage
 ])
 def test_cov_exact_engine_fused_kernel_equals_two_kernel_path(dev, monkeypatch, n, f, lag, block, ld_pad, standardise):
     """tc_i8x3 has two implementations of the same integer arithmetic: quantise kernel + contraction kernel
