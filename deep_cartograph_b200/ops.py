@@ -206,10 +206,14 @@ def lagged_covariance(X: torch.Tensor, lag: int, mean: Optional[torch.Tensor] = 
     lib = _lib.load()
     dev = X.device
     want_st = want_st and lag > 0
-    S0 = torch.empty((f, f), dtype=torch.float64, device=dev) if want_s0 else None
-    St = torch.empty((f, f), dtype=torch.float64, device=dev) if want_st else None
-    a = torch.empty(f, dtype=torch.float64, device=dev)
-    b = torch.empty(f, dtype=torch.float64, device=dev)
+    # one flat buffer [S0 | St | a | b | M]: the frame-sharded path all-reduces it in place (no packing copy)
+    n0, nt = (f * f if want_s0 else 0), (f * f if want_st else 0)
+    flat = torch.empty(n0 + nt + 2 * f + 1, dtype=torch.float64, device=dev)
+    S0 = flat[:n0].view(f, f) if want_s0 else None
+    St = flat[n0:n0 + nt].view(f, f) if want_st else None
+    a = flat[n0 + nt:n0 + nt + f]
+    b = flat[n0 + nt + f:n0 + nt + 2 * f]
+    flat[-1:].fill_(float(n - lag))
     if eng == _lib.COV_TC_I8X3:
         if xmin is None or xmax is None:
             xmin, xmax = X.amin(dim=0), X.amax(dim=0)
@@ -221,13 +225,13 @@ def lagged_covariance(X: torch.Tensor, lag: int, mean: Optional[torch.Tensor] = 
               xmin.contiguous().data_ptr(), xmax.contiguous().data_ptr(), block, _ptr(S0), _ptr(St),
               a.data_ptr(), b.data_ptr(), info.data_ptr(), ws.data_ptr(), ws.numel(), _stream(X.device))
         _count(5)                                      # prep + plan + quantise + contraction + column sums (per window)
-        return {"S0": S0, "St": St, "a": a, "b": b, "M": n - lag, "clamped": info}
+        return {"S0": S0, "St": St, "a": a, "b": b, "M": n - lag, "clamped": info, "flat": flat}
     ws = _ws(lib.dcg_cov_workspace_bytes(n, f, lag, block, eng), dev)
     _call(X.device, "dcg_cov_lag_f32", X.data_ptr(), n, f, ld, lag, _ptr(mean), _ptr(rng), block,
               _ptr(S0), _ptr(St), a.data_ptr(), b.data_ptr(), eng, ws.data_ptr(), ws.numel(),
               _stream(X.device))
     _count(2 if eng == _lib.COV_SIMT_F32 else 3)      # colsum + engine (+ split reduction)
-    return {"S0": S0, "St": St, "a": a, "b": b, "M": n - lag}
+    return {"S0": S0, "St": St, "a": a, "b": b, "M": n - lag, "flat": flat}
 
 
 def cov_i8_timing(on: Optional[bool] = None):

@@ -121,6 +121,27 @@ class FrameShards:
         number of lagged pairs, n_total - lag) saves the host read of the reduced M."""
         keys = [k for k in ("S0", "St", "a", "b") if s.get(k) is not None]
         dev = s["a"].device
+        flat = s.get("flat")
+
+        def _views_of_flat():
+            # the dict's tensors must still BE the slices of `flat` (a caller may have replaced one, e.g. after
+            # re-standardising speculative sums): otherwise pack as usual
+            if flat is None or flat.numel() != sum(s[k].numel() for k in keys) + 1:
+                return False
+            o = 0
+            for k in keys:
+                if s[k].data_ptr() != flat.data_ptr() + 8 * o or not s[k].is_contiguous():
+                    return False
+                o += s[k].numel()
+            return True
+
+        if _views_of_flat():
+            # ops.lagged_covariance laid the sums out as one buffer [S0 | St | a | b | M]: reduce it in place
+            flat[-1:].fill_(float(s["M"]))
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            out = dict(s)
+            out["M"] = int(m_total) if m_total is not None else int(round(float(flat[-1].item())))
+            return out
         flat = torch.cat([s[k].reshape(-1) for k in keys] +
                          [torch.tensor([float(s["M"])], dtype=torch.float64, device=dev)])
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
