@@ -89,9 +89,9 @@ def test_sharded_statistics_pack_and_merge_kernels(dev):
     assert float(m["n"].item()) == n
     np.testing.assert_allclose(m["mean"].cpu().numpy(), whole["mean"], rtol=2e-6, atol=1e-7)
     np.testing.assert_allclose(np.sqrt(m["m2"].cpu().numpy() / (n - 1)), whole["std"], rtol=2e-6)
-    one = ops.column_stats(Xd)                             # and == the single-launch statistics to FP64 rounding
-    np.testing.assert_allclose(m["mean"].cpu().numpy(), one["mean"].cpu().numpy(), rtol=1e-9, atol=1e-10)
-    np.testing.assert_allclose(m["m2"].cpu().numpy(), one["m2"].cpu().numpy(), rtol=1e-7)
+    one = ops.column_stats(Xd)        # and == the single-launch statistics (per-thread partial sums are shifted FP32)
+    np.testing.assert_allclose(m["mean"].cpu().numpy(), one["mean"].cpu().numpy(), rtol=1e-7, atol=1e-8)
+    np.testing.assert_allclose(m["m2"].cpu().numpy(), one["m2"].cpu().numpy(), rtol=1e-6)
     np.testing.assert_array_equal(m["min"].cpu().numpy(), whole["min"].astype(np.float32))
     np.testing.assert_array_equal(m["max"].cpu().numpy(), whole["max"].astype(np.float32))
 
