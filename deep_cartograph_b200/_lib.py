@@ -30,6 +30,11 @@ _SIGNATURES = {
     "dcg_device_info": (_c_int, [C.POINTER(_c_int)] * 3),
     "dcg_colstats_workspace_bytes": (_c_sz, [_c_i64, _c_int]),
     "dcg_colstats_f32": (_c_int, [_p, _c_i64, _c_int, _c_i64, _p, _p, _p, _p, _p, _c_sz, _p]),
+    "dcg_p2p_buffer_bytes": (_c_sz, [_c_int, _c_i64]),
+    "dcg_p2p_alloc": (_c_int, [_c_sz, _p, _p]),
+    "dcg_p2p_open": (_c_int, [_p, _p]),
+    "dcg_p2p_close": (_c_int, [_p, _c_int]),
+    "dcg_p2p_allreduce_f64": (_c_int, [_p, _p, _c_int, _c_int, _c_int, _c_int, _p, _c_i64, C.c_uint64, _p]),
     "dcg_stats_pack": (_c_int, [C.c_double, _p, _p, _p, _p, _c_int, _p, _p]),
     "dcg_stats_merge": (_c_int, [_p, _c_int, _c_int, _p, _p, _p, _p, _p, _p]),
     "dcg_standardize_f32": (_c_int, [_p, _c_i64, _c_int, _c_i64, _p, _p, _p]),

@@ -13,10 +13,70 @@ frames, so the data path needs exactly three exchanges, all issued through
 """
 from __future__ import annotations
 
+import ctypes
+import logging
+import os
 from typing import Optional, Tuple
 
 import torch
 import torch.distributed as dist
+
+logger = logging.getLogger(__name__)
+
+# doubles per rank and exchange of the peer-memory all-reduce (KMeans k = 1000, d = 10 packs 11 003)
+_P2P_SLOT_DOUBLES = 16384
+
+
+class PeerAllReduce:
+    """The small all-reduces of the sharded path as ONE kernel per GPU over NVLink peer memory
+    (``csrc/p2p.cu``: push into every peer's inbox, flags, reduce in rank order) instead of an NCCL call
+    each: at a few KB these are pure latency.  Built collectively (every rank of the group must construct
+    it); inboxes are cudaMalloc allocations shared through CUDA IPC handles."""
+
+    def __init__(self, group, rank: int, world: int, device: torch.device):
+        from . import _lib
+        self._lib = _lib
+        lib = _lib.load()
+        self.rank, self.world, self.device = rank, world, device
+        self.slot = _P2P_SLOT_DOUBLES
+        nbytes = lib.dcg_p2p_buffer_bytes(world, self.slot)
+        if nbytes == 0:
+            raise RuntimeError("peer all-reduce: world size out of range")
+        own = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * 64)()
+        with torch.cuda.device(device):
+            _lib.check("dcg_p2p_alloc", lib.dcg_p2p_alloc(nbytes, ctypes.byref(own), handle))
+            handles = [None] * world
+            dist.all_gather_object(handles, bytes(handle), group=group)
+            self._bases = (ctypes.c_void_p * world)()
+            self._opened = []
+            for r in range(world):
+                if r == rank:
+                    self._bases[r] = own.value
+                    continue
+                peer = ctypes.c_void_p()
+                buf = (ctypes.c_ubyte * 64).from_buffer_copy(handles[r])
+                _lib.check("dcg_p2p_open", lib.dcg_p2p_open(buf, ctypes.byref(peer)))
+                self._bases[r] = peer.value
+                self._opened.append(peer.value)
+        self._own = own.value
+        self.seq = 0
+        dist.barrier(group=group)            # every inbox is mapped (and zeroed) before the first exchange
+
+    def allreduce_(self, t: torch.Tensor, op: int) -> torch.Tensor:
+        """In-place SUM (op 0) / MAX (op 1) of a contiguous float64 CUDA tensor of at most ``slot`` elements."""
+        self.seq += 1
+        lib = self._lib.load()
+        with torch.cuda.device(t.device):
+            self._lib.check("dcg_p2p_allreduce_f64",
+                            lib.dcg_p2p_allreduce_f64(t.data_ptr(), t.data_ptr(), t.numel(), op, self.rank, self.world,
+                                                      self._bases, self.slot, self.seq,
+                                                      torch.cuda.current_stream(t.device).cuda_stream))
+        return t
+
+    def fits(self, t: torch.Tensor) -> bool:
+        return (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and 0 < t.numel() <= self.slot
+                and t.device == self.device)
 
 
 def shard_range(n_total: int, rank: int, world: int) -> Tuple[int, int]:
@@ -33,6 +93,29 @@ class FrameShards:
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
+        self._peer = None                    # PeerAllReduce, built on first use (collectively)
+        self._peer_failed = False
+
+    def _peer_allreduce(self, t: torch.Tensor):
+        """The peer-memory all-reduce object when ``t`` qualifies (CUDA, NCCL group on one box, few KB), else None.
+        ``DCG_P2P_ALLREDUCE=0`` keeps every exchange on NCCL.  The decision depends only on properties that are
+        equal on all ranks (backend, world size, dtype, element count), so it is collective."""
+        if (self._peer_failed or self.world < 2 or not t.is_cuda or t.dtype != torch.float64
+                or t.numel() > _P2P_SLOT_DOUBLES or t.numel() == 0 or not t.is_contiguous()
+                or os.environ.get("DCG_P2P_ALLREDUCE", "1") == "0" or dist.get_backend(self.group) != "nccl"):
+            return None
+        if self._peer is None:
+            ok = torch.ones(1, dtype=torch.int32, device=t.device)
+            try:
+                self._peer = PeerAllReduce(self.group, self.rank, self.world, t.device)
+            except Exception as exc:          # no IPC / peer access on this box: NCCL for everything
+                logger.warning("peer-memory all-reduce unavailable (%s); using NCCL", exc)
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)      # all ranks or none
+            if int(ok.item()) == 0:
+                self._peer, self._peer_failed = None, True
+                return None
+        return self._peer
 
     # ---- statistics ---------------------------------------------------------------------------
     def merge_stats(self, st: dict, n_total: Optional[int] = None) -> dict:
@@ -158,10 +241,18 @@ class FrameShards:
         """Global per-column min and max in ONE collective: MAX over [-min | max]."""
         d = mn.numel()
         buf = torch.cat([-mn, mx])
-        dist.all_reduce(buf, op=dist.ReduceOp.MAX, group=self.group)
+        b64 = buf.to(torch.float64)
+        peer = self._peer_allreduce(b64)
+        if peer is not None:
+            buf = peer.allreduce_(b64, 1).to(buf.dtype)      # float32 -> float64 -> float32 is exact
+        else:
+            dist.all_reduce(buf, op=dist.ReduceOp.MAX, group=self.group)
         return -buf[:d], buf[d:]
 
     def allreduce_sum_(self, t: torch.Tensor) -> torch.Tensor:
+        peer = self._peer_allreduce(t)
+        if peer is not None:
+            return peer.allreduce_(t, 0)
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
         return t
 

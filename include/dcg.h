@@ -69,6 +69,22 @@ int dcg_stats_pack(double n, const double* mean, const double* m2, const float* 
 int dcg_stats_merge(const double* all_packed, int world, int f, double* mean, double* m2,
                     float* minv, float* maxv, double* n_total, void* stream);
 
+/* ---- small all-reduce over NVLink peer memory ----------------------------------------
+ * The frame-sharded path exchanges a few KB per Lloyd iteration ([sums | counts | stats], reference
+ * statistics.py:189-195 run on shards), per projection pass (the CV min / max of normalize_cv,
+ * cv_calculator.py:974-991) and per KMeans set-up.  These are ONE kernel per GPU working on peer memory:
+ * every rank stores its vector into its slot of every peer's inbox, releases a flag, waits for the `world`
+ * flags of its own inbox and reduces the slots in rank order (bitwise identical results on all ranks).
+ * One process per GPU: dcg_p2p_alloc makes this rank's inbox (dcg_p2p_buffer_bytes) and its 64-byte CUDA IPC
+ * handle, dcg_p2p_open maps a peer's; `peer_bases` (host array, world entries, own inbox at [rank]);
+ * `seq` = 1, 2, 3, ... identical on all ranks; op 0 = sum, 1 = max; n <= slot_doubles; in place allowed.   */
+size_t dcg_p2p_buffer_bytes(int world, int64_t slot_doubles);
+int dcg_p2p_alloc(size_t bytes, void** ptr, unsigned char* handle64);
+int dcg_p2p_open(const unsigned char* handle64, void** ptr);
+int dcg_p2p_close(void* ptr, int opened);
+int dcg_p2p_allreduce_f64(const double* v, double* out, int n, int op, int rank, int world,
+                          void* const* peer_bases, int64_t slot_doubles, uint64_t seq, void* stream);
+
 /* ---- A4: in-place standardisation ------------------------------------------------------------
  * Replaces `LinearCalculator.normalize_data` (cv_calculator.py:806-837): x = (x - mean[j]) /
  * range[j] with IEEE float32 subtraction and division.  Also used for the CV normalisation of

@@ -54,6 +54,28 @@ def main():
     calc3.load_training_tensor(Xloc, shards=shards)
     calc3.create_output_folders(); calc3.compute_cv()
 
+    # ---- the peer-memory all-reduce (csrc/p2p.cu) against NCCL: sums and maxima, sizes from 1 element to a full
+    #      slot, many exchanges in a row (both inbox parities, ranks running ahead of each other)
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    for it, nel in enumerate([1, 5, 403, 11_003, 16_384, 7, 7, 7, 7, 1000]):
+        v = torch.randn(nel, generator=g, dtype=torch.float64, device=dev)
+        for op, red in ((0, dist.ReduceOp.SUM), (1, dist.ReduceOp.MAX)):
+            want = v.clone()
+            dist.all_reduce(want, op=red)
+            peer = shards._peer_allreduce(v)
+            assert peer is not None, "peer-memory all-reduce unavailable on this box"
+            got = peer.allreduce_(v.clone(), op)
+            if op == 1:
+                assert torch.equal(got, want), (it, nel)
+            else:
+                assert torch.allclose(got, want, rtol=1e-14, atol=1e-14), (it, nel)
+            # every rank holds bitwise the same result
+            chk = got.clone()
+            dist.broadcast(chk, 0)
+            assert torch.equal(chk, got), (it, nel, "ranks differ")
+        if rank == it % world:
+            torch.cuda._sleep(2_000_000)              # skew the ranks
+
     # ---- KMeans: same frames on every path (rank 0 draws them); cluster 5 starts empty
     k, dk, nk = 6, 3, 50_003
     Y = cluster_points(nk, dk, 5, dev, seed=11, dtype=torch.float64).round(decimals=4)
