@@ -166,13 +166,37 @@ __device__ __forceinline__ uint32_t pack_byte(int a, int b, int c, int d) {
   const uint32_t hi = __byte_perm((uint32_t)c, (uint32_t)d, ((4 + K) << 4) | K);
   return __byte_perm(lo, hi, 0x5410);
 }
-// Balanced base-256 digits of four integers (|q| < 2^23), one word per digit:
+// Balanced base-256 digits of an integer q (|q| < 2^23):
 //   d0 = byte 0 of q,  d1 = byte 0 of (q + 128) >> 8 = byte 1 of q + 128,
 //   d2 = byte 0 of (((q + 128) >> 8) + 128) >> 8 = byte 2 of q + 128 + 32768      (floors nest)
-__device__ __forceinline__ void digits4(const int (&q)[4], uint32_t& w0, uint32_t& w1, uint32_t& w2) {
-  w0 = pack_byte<0>(q[0], q[1], q[2], q[3]);
-  w1 = pack_byte<1>(q[0] + 128, q[1] + 128, q[2] + 128, q[3] + 128);
-  w2 = pack_byte<2>(q[0] + 32896, q[1] + 32896, q[2] + 32896, q[3] + 32896);
+// (digits4_biased below works on q + 0x8080, where all three are plain bytes up to a flipped top bit)
+
+// q + kDigitBias by the float "magic number" rounding (RN-even like __float2int_rn, on the full-rate FP pipe):
+// |y| <= kQMax < 2^22, so y + 1.5 2^23 has unit spacing and its mantissa bits are the integer.
+constexpr int kDigitBias = 0x8080;
+// y = (x - c) 2^e as ONE fused multiply-add, x 2^e - c 2^e: both products are exact (i8_prep_kernel keeps c 2^e
+// finite), so the single rounding is the rounding of the reference's float32 subtraction, scaled.
+// The symmetric clamp is one instruction (min of the magnitudes, sign of y).
+__device__ __forceinline__ float clamp_sym(float y) {
+  float r;
+  asm("min.xorsign.abs.f32 %0, %1, %2;" : "=f"(r) : "f"(y), "f"((float)kQMax));
+  return r;
+}
+__device__ __forceinline__ float max3_abs(float a, float y0, float y1) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(fabsf(y0)), "f"(fabsf(y1)));
+  return r;
+}
+__device__ __forceinline__ int quantize_biased(float y) {
+  return __float_as_int(clamp_sym(y) + 12582912.f) - (0x4B400000 - kDigitBias);
+}
+// balanced digits of four biased integers q' = q + 0x8080 (digits4 above adds 128 / 32896 per digit):
+//   d0 = byte 0 of q = byte 0 of q' with its top bit flipped, d1 = byte 1 of q + 128 = byte 1 of q' with its top
+//   bit flipped, d2 = byte 2 of q + 32896 = byte 2 of q'
+__device__ __forceinline__ void digits4_biased(int a, int b, int c, int d, uint32_t& w0, uint32_t& w1, uint32_t& w2) {
+  w0 = pack_byte<0>(a, b, c, d) ^ 0x80808080u;
+  w1 = pack_byte<1>(a, b, c, d) ^ 0x80808080u;
+  w2 = pack_byte<2>(a, b, c, d);
 }
 
 // planes: [set (Z, U)][digit 0..2][feature][frame], frame stride 1, feature stride wpad, digit stride
@@ -234,31 +258,40 @@ i8_quantize_kernel(const float* __restrict__ X, int64_t row0, int64_t pairs, int
         }
       }
       const int w = 16 * h + frq;
+      float amax = 0.f;
 #pragma unroll
       for (int v = 0; v < 4; ++v) {
+        // biased integers q + 0x8080 (quantize_biased), one FMA + clamp + magic-number rounding per value
         int q[4], u[4];
         int ps = 0, pl = 0;                              // |q| < 2^22: four of them fit an int
+        const float ncm = -c[v] * m[v];
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-          q[r] = quantize1(x[r][v], c[v], m[v], clamped);
+          const float y = fmaf(x[r][v], m[v], ncm);
+          q[r] = quantize_biased(y);
           ps += q[r];
           if (WITH_U) {
-            const int ql = quantize1(xl[r][v], c[v], m[v], clamped);
+            const float yl = fmaf(xl[r][v], m[v], ncm);
+            amax = max3_abs(amax, y, yl);
+            const int ql = quantize_biased(yl);
             pl += ql;
-            u[r] = q[r] + ql;
+            u[r] = q[r] + ql - kDigitBias;
+          } else {
+            amax = fmaxf(amax, fabsf(y));
           }
         }
-        acc_t[v] += ps;
-        if (WITH_U) acc_l[v] += pl;
+        acc_t[v] += ps - 4 * kDigitBias;
+        if (WITH_U) acc_l[v] += pl - 4 * kDigitBias;
         const int fe = 4 * fe4 + v;
         uint32_t w0, w1, w2;
-        digits4(q, w0, w1, w2);
+        digits4_biased(q[0], q[1], q[2], q[3], w0, w1, w2);
         tile[0][fe][w] = w0; tile[1][fe][w] = w1; tile[2][fe][w] = w2;
         if (WITH_U) {
-          digits4(u, w0, w1, w2);
+          digits4_biased(u[0], u[1], u[2], u[3], w0, w1, w2);
           tile[3][fe][w] = w0; tile[4][fe][w] = w1; tile[5][fe][w] = w2;
         }
       }
+      clamped += amax > (float)kQMax + 0.5f;             // groups of 4 x 4 values that held a clamped one
     }
     __syncthreads();
     // (3 or 6) planes x 64 features x 128 bytes -> global, 16 bytes per thread and step, 128-byte lines
@@ -681,34 +714,6 @@ __device__ __forceinline__ int win_stages(const ParamsF& p, int w, int split) {
   if (rem <= 0) return 0;
   const int64_t st = (rem + kStageFrames - 1) / kStageFrames;
   return (int)(st < p.share_stages ? st : p.share_stages);
-}
-
-// q + kDigitBias by the float "magic number" rounding (RN-even like __float2int_rn, on the full-rate FP pipe):
-// |y| <= kQMax < 2^22, so y + 1.5 2^23 has unit spacing and its mantissa bits are the integer.
-constexpr int kDigitBias = 0x8080;
-// y = (x - c) 2^e as ONE fused multiply-add, x 2^e - c 2^e: both products are exact (i8_prep_kernel keeps c 2^e
-// finite), so the single rounding is the rounding of the reference's float32 subtraction, scaled.
-// The symmetric clamp is one instruction (min of the magnitudes, sign of y).
-__device__ __forceinline__ float clamp_sym(float y) {
-  float r;
-  asm("min.xorsign.abs.f32 %0, %1, %2;" : "=f"(r) : "f"(y), "f"((float)kQMax));
-  return r;
-}
-__device__ __forceinline__ float max3_abs(float a, float y0, float y1) {
-  float r;
-  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(fabsf(y0)), "f"(fabsf(y1)));
-  return r;
-}
-__device__ __forceinline__ int quantize_biased(float y) {
-  return __float_as_int(clamp_sym(y) + 12582912.f) - (0x4B400000 - kDigitBias);
-}
-// balanced digits of four biased integers q' = q + 0x8080 (digits4 above adds 128 / 32896 per digit):
-//   d0 = byte 0 of q = byte 0 of q' with its top bit flipped, d1 = byte 1 of q + 128 = byte 1 of q' with its top
-//   bit flipped, d2 = byte 2 of q + 32896 = byte 2 of q'
-__device__ __forceinline__ void digits4_biased(int a, int b, int c, int d, uint32_t& w0, uint32_t& w1, uint32_t& w2) {
-  w0 = pack_byte<0>(a, b, c, d) ^ 0x80808080u;
-  w1 = pack_byte<1>(a, b, c, d) ^ 0x80808080u;
-  w2 = pack_byte<2>(a, b, c, d);
 }
 
 template <bool WITH_LAG>
