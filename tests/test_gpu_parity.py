@@ -268,6 +268,48 @@ def test_cov_exact_engine_fused_kernel_equals_two_kernel_path(dev, monkeypatch, 
     assert torch.equal(out["2"]["a"], out["0"]["a"]) and torch.equal(out["2"]["b"], out["0"]["b"])
 
 
+@pytest.mark.parametrize("fused", ["2", "0"])
+@pytest.mark.parametrize("n,f,lag,block", [(3000, 300, 7, 0), (1500, 2000, 10, 0), (2000, 990, 5, 99), (1000, 331, 0, 0),
+                                           (130, 1000, 1, 0)])
+def test_cov_exact_engine_stays_inside_its_workspace(dev, monkeypatch, fused, n, f, lag, block):
+    """The exact engine's workspace (digit-plane ring or window, tables, counters) between two canary regions:
+    nothing outside the `dcg_cov_i8_workspace_bytes` bytes handed over may be written, by either implementation
+    (fused persistent kernel / quantise + contraction kernels), and the outputs must not depend on what the
+    workspace held before."""
+    from deep_cartograph_b200 import ops, _lib
+    monkeypatch.setenv("DCG_I8_FUSED", fused)
+    lib = _lib.load()
+    X = _cuda(synth_features(n, f, seed=n + f), dev)
+    st = ops.column_stats(X)
+    mean, rng = st["mean"].float(), torch.sqrt(st["m2"] / (n - 1)).float()
+    nbytes = int(lib.dcg_cov_i8_workspace_bytes(n, f, lag, block))
+    assert nbytes > 0
+    guard = 1 << 20
+    outs = []
+    for fill in (0xA5, 0x00):
+        buf = torch.full((nbytes + 2 * guard,), 0x5A, dtype=torch.uint8, device=dev)
+        buf[guard:guard + nbytes] = fill
+        S0 = torch.empty((f, f), dtype=torch.float64, device=dev)
+        St = torch.empty((f, f), dtype=torch.float64, device=dev) if lag > 0 else None
+        a, b = (torch.empty(f, dtype=torch.float64, device=dev) for _ in range(2))
+        info = torch.empty(1, dtype=torch.int32, device=dev)
+        ops._call(dev, "dcg_cov_lag_i8_f32", X.data_ptr(), n, f, X.stride(0), lag, mean.data_ptr(), rng.data_ptr(),
+                  st["min"].data_ptr(), st["max"].data_ptr(), block, S0.data_ptr(), St.data_ptr() if lag > 0 else None,
+                  a.data_ptr(), b.data_ptr(), info.data_ptr(), buf.data_ptr() + guard, nbytes,
+                  torch.cuda.current_stream(dev).cuda_stream)
+        torch.cuda.synchronize()
+        assert bool((buf[:guard] == 0x5A).all()) and bool((buf[guard + nbytes:] == 0x5A).all()), "canary overwritten"
+        assert int(info.item()) == 0
+        outs.append((torch.triu(S0), St, a, b))
+    for u, v in zip(outs[0], outs[1]):
+        if u is not None:
+            if block and u.dim() == 2:
+                blk = torch.arange(f, device=dev) // block
+                m = blk[:, None] == blk[None, :]
+                u, v = torch.where(m, u, torch.zeros_like(u)), torch.where(m, v, torch.zeros_like(v))
+            torch.testing.assert_close(u, v, rtol=1e-13, atol=1e-9)
+
+
 @pytest.mark.parametrize("engine", ["tc_3xf16", "tc_3xtf32"])
 def test_cov_split_precision_edge_columns(dev, engine):
     """Columns that stress the split-precision operands: a constant feature (range -> 1, z = 0), a
