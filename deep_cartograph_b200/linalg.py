@@ -33,6 +33,50 @@ EIG_STATS = {"fast": 0, "dense": 0, "last_iters": 0}
 _PARTIAL_MIN_F = 192
 
 
+def _tri_inv_lower(L: torch.Tensor) -> torch.Tensor:
+    """Inverse of a batch of lower-triangular matrices (nb, F, F), FP64.
+
+    cuBLAS ``trsm`` with F right-hand sides is a panel-serial algorithm whose time is linear in F at these
+    sizes (0.54 ms at F = 1000, 0.064 ms at F = 125, measured: ``tools_dev/tri_time.py``), but it batches for
+    free.  So the diagonal is cut into 8 blocks that are inverted as ONE batched call, and the inverse is
+    assembled bottom-up from  [[A, 0], [B, C]]^-1 = [[A^-1, 0], [-C^-1 B A^-1, C^-1]]  with batched products
+    (three levels): 0.2 ms at F = 1000.  Sizes that are not a multiple of the block count are padded with an
+    identity block."""
+    nb, F = L.shape[0], L.shape[-1]
+    if F < 256:
+        eye = torch.eye(F, dtype=L.dtype, device=L.device)
+        return torch.linalg.solve_triangular(L, eye.expand(nb, F, F), upper=False)
+    nblk = 8 if F >= 512 else 4
+    bs = -(-F // nblk)
+    Fp = bs * nblk
+    if Fp != F:
+        Lp = torch.eye(Fp, dtype=L.dtype, device=L.device).repeat(nb, 1, 1)
+        Lp[:, :F, :F] = L
+    else:
+        Lp = L
+    # diagonal blocks as one batch
+    D = Lp.view(nb, nblk, bs, nblk, bs).diagonal(dim1=1, dim2=3).permute(0, 3, 1, 2)         # (nb, nblk, bs, bs)
+    out = torch.zeros_like(Lp)
+    if Lp.is_cuda and bs <= 128:
+        # one CTA per diagonal block, forward substitution (csrc/eig_dense.cu): cuBLAS' batched trsm loops over
+        # the blocks, 56 us each
+        from . import ops
+        ops.tri_inv_blocks_(Lp, out, nblk, bs)
+    else:
+        eye = torch.eye(bs, dtype=L.dtype, device=L.device)
+        Dinv = torch.linalg.solve_triangular(D.reshape(nb * nblk, bs, bs), eye.expand(nb * nblk, bs, bs), upper=False)
+        out.view(nb, nblk, bs, nblk, bs).diagonal(dim1=1, dim2=3).copy_(Dinv.view(nb, nblk, bs, bs).permute(0, 2, 3, 1))
+    s, npairs = bs, nblk // 2
+    while npairs >= 1:
+        # super-blocks of size 2s on the diagonal: their halves are inverted already
+        O = out.view(nb, npairs, 2 * s, npairs, 2 * s).diagonal(dim1=1, dim2=3).permute(0, 3, 1, 2)   # views
+        S = Lp.view(nb, npairs, 2 * s, npairs, 2 * s).diagonal(dim1=1, dim2=3).permute(0, 3, 1, 2)
+        lower = -(O[..., s:, s:] @ (S[..., s:, :s] @ O[..., :s, :s]))
+        O[..., s:, :s] = lower
+        s, npairs = 2 * s, npairs // 2
+    return out[:, :F, :F] if Fp != F else out
+
+
 def _shift_invert_topk(B: torch.Tensor, Ct: torch.Tensor, out: int, tol: float = 1e-12,
                        max_rounds: int = 10):
     """The `out` largest eigenpairs of Ct v = lambda B v (B SPD) by shift-and-invert subspace
@@ -56,83 +100,22 @@ def _shift_invert_topk(B: torch.Tensor, Ct: torch.Tensor, out: int, tol: float =
         B, Ct = B.unsqueeze(0), Ct.unsqueeze(0)
     nb, F = B.shape[0], B.shape[-1]
     b = min(F, out + 8)
-    nrm = torch.linalg.matrix_norm(Ct).unsqueeze(-1)         # (nb, 1) Frobenius norms, residual scale
-    eye = torch.eye(F, dtype=B.dtype, device=B.device)
-    eye_b = torch.eye(b, dtype=B.dtype, device=B.device)
 
-    def factor(sig, check=True):
-        """sig: (nb, 1, 1).  Returns (K, K^-1, K^-1 B, info) or None if any K is not positive definite.
-        ``check=False`` skips the host read of the factorisation status (the caller reads ``info`` later,
-        together with the residuals: a failed factor shows there before any result is accepted)."""
-        Kmat = sig * B - Ct
-        Lk, info = torch.linalg.cholesky_ex(Kmat)
-        if check and int(info.abs().max().item()) != 0:
-            return None
-        Li = torch.linalg.solve_triangular(Lk, eye.expand(nb, F, F), upper=False)
-        Kinv = Li.mT @ Li                       # two F^3 products (70 us each at F = 1000) buy 1 instead of 6
-        return Kmat, Kinv, Kinv @ B, info       # skinny products per cheap step, 4 per accurate one
-
-    sigma = torch.full((nb, 1, 1), 1.05, dtype=B.dtype, device=B.device)
-    # the first factorisation is used unchecked: its status rides on the first round's host read
-    fac = factor(sigma, check=False)
-    pending_info = fac[3]
-
-    def step_cheap(Xc):
-        """X <- (K^-1 B) X with the explicitly formed operator: one product.  Its rounding (eps cond(K)) perturbs
-        the operator, not the convergence: used for the first steps only, the accurate steps that follow
-        converge to the eigenvectors of the true pencil."""
-        return fac[2] @ Xc
-
-    def solve(Z):
-        Kmat, Kinv = fac[0], fac[1]
-        Y = Kinv @ Z
-        # one step of iterative refinement against K itself
-        return torch.baddbmm(Y, Kinv, torch.baddbmm(Z, Kmat, Y, alpha=-1.0))
-
-    X = _start_block(F, b, B.device).expand(nb, F, b)
-    it = 0
+    # round 0 (factorisation at sigma = 1.05, 12 steps, Rayleigh-Ritz, residuals) is a fixed sequence of ~150
+    # small launches with no host read inside: on the GPU it is replayed as ONE CUDA graph (the stage is
+    # host-launch-bound otherwise: 2.4 ms of wall time for ~1.5 ms of GPU time at F = 1000)
+    st = _first_round(B, Ct, out, b)
+    B, Ct = st["B"], st["Ct"]
+    fac, X, theta, sigma, nrm = st["fac"], st["X"], st["theta"], st["sigma"], st["nrm"]
+    hostvec = st["host"]
+    it = _ROUND0_STEPS
     reshifted = False
     for rnd in range(max_rounds):
-        # the first Rayleigh-Ritz after 12 steps (8 are rarely enough for 1e-12, and a Ritz step with its
-        # small eigen-solve, residual and host read costs as much as 4 iterations); columns are rescaled every
-        # other step (the iteration amplifies by at most 1 / (sigma - lambda_max) per step)
-        for i in range(12 if rnd == 0 else 4):
-            X = step_cheap(X) if (rnd == 0 and i < 8) else solve(B @ X)
-            if i & 1:
-                X = X / torch.linalg.norm(X, dim=-2, keepdim=True)
-            if i & 3 == 3 and rnd == 0 and i < 11:
-                # re-orthogonalise every 4 steps (Cholesky QR, no host read): the noise directions shrink by
-                # (sigma - lambda_max) / sigma per step, so after 8 plain steps the block would be
-                # numerically rank deficient
-                G = X.mT @ X
-                Lg, _ = torch.linalg.cholesky_ex(0.5 * (G + G.mT))
-                X = torch.linalg.solve_triangular(Lg.mT, X, upper=True, left=False)      # X <- X Lg^-T
-            it += 1
-        # Rayleigh-Ritz in span(X):  (X^T Ct X) s = theta (X^T B X) s
-        BX = B @ X
-        CX = Ct @ X
-        Gb = X.mT @ BX
-        if X.is_cuda and b <= 32:
-            # the b x b pencil in one launch (Cholesky + Jacobi), its status rides on the host read below
-            from . import ops
-            theta, S, bad = ops.gen_eig_small(X.mT @ CX, Gb)
-        else:
-            Lb, info = torch.linalg.cholesky_ex(0.5 * (Gb + Gb.mT))
-            if int(info.abs().max().item()) != 0:
-                return None
-            Lbi = torch.linalg.solve_triangular(Lb, eye_b.expand(nb, b, b), upper=False)
-            Hs = Lbi @ (X.mT @ CX) @ Lbi.mT
-            theta, S = torch.linalg.eigh(0.5 * (Hs + Hs.mT))
-            theta = theta.flip(-1)
-            S = Lbi.mT @ S.flip(-1)
-            bad = torch.zeros(nb, dtype=B.dtype, device=B.device)
-        X = X @ S
-        res = torch.linalg.norm(CX @ S[..., :out] - (BX @ S[..., :out]) * theta[:, None, :out], dim=-2)
-        rel = res / (nrm * torch.linalg.norm(X[..., :out], dim=-2))
+        if rnd > 0:
+            X, theta, hostvec = _round_on_device(B, Ct, nrm, fac, X, sigma, None, out, 4, False)
+            it += 4
         # one host read per round: worst residual + the Ritz values the shift logic needs
-        host = torch.cat([rel.max().reshape(1), theta[:, 0], theta[:, out - 1], theta[:, b - 1],
-                          sigma.reshape(-1), bad.max().reshape(1),
-                          pending_info.abs().max().to(B.dtype).reshape(1)]).tolist()
+        host = hostvec.tolist()
         if host[-1] != 0:
             # sigma = 1.05 was not above the spectrum: checked factorisations with larger shifts, start over
             if rnd > 0:
@@ -140,23 +123,26 @@ def _shift_invert_topk(B: torch.Tensor, Ct: torch.Tensor, out: int, tol: float =
             fac = None
             for _ in range(2):
                 sigma = sigma * 2.0
-                fac = factor(sigma)
+                fac = _factor(B, Ct, sigma, check=True)
                 if fac is not None:
                     break
             if fac is None:
                 return None
-            pending_info = torch.zeros_like(pending_info)
             X = _start_block(F, b, B.device).expand(nb, F, b)
-            it = 0
+            X, theta, hostvec = _round_on_device(B, Ct, nrm, fac, X, sigma, None, out, _ROUND0_STEPS, True)
+            host = hostvec.tolist()
+            if host[-1] != 0:
+                return None
             reshifted = True                   # no second re-shift on this path
-            continue
         if host[-2] != 0 or host[0] != host[0]:
             return None
         worst = host[0]
+        if os.environ.get("DCG_EIG_DEBUG"):
+            print(f"[dcg eig] round {rnd}: {it} steps, worst relative residual {worst:.3e} (tol {tol:.1e})", flush=True)
         if worst <= tol:
             EIG_STATS["fast"] += nb
             EIG_STATS["last_iters"] = it
-            ev, V = theta[:, :out], X[..., :out]
+            ev, V = theta[:, :out].clone(), X[..., :out].clone()
             return (ev, V) if batched else (ev[0], V[0])
         if not reshifted:
             reshifted = True
@@ -170,16 +156,135 @@ def _shift_invert_topk(B: torch.Tensor, Ct: torch.Tensor, out: int, tol: float =
                 for mult in (0.05, 0.2, 0.8):
                     s2 = [min(sig[i], th0[i] + mult * max(th0[i] - thb[i], 1e-12) + 1e-9 * max(1.0, abs(th0[i])))
                           for i in range(nb)]
-                    f2 = factor(torch.tensor(s2, dtype=B.dtype, device=B.device).reshape(nb, 1, 1))
+                    s2t = torch.tensor(s2, dtype=B.dtype, device=B.device).reshape(nb, 1, 1)
+                    f2 = _factor(B, Ct, s2t, check=True)
                     if f2 is not None:
-                        fac, sig = f2, s2
-                        sigma = torch.tensor(s2, dtype=B.dtype, device=B.device).reshape(nb, 1, 1)
+                        fac, sig, sigma = f2, s2, s2t
                         break
             # flat spectrum below the wanted eigenvalues: more steps than the dense route costs
             rate = worst_rate(sig)
             if rate >= 1.0 or math.log(tol) / math.log(max(rate, 1e-300)) > 4 * max_rounds:
                 return None
     return None
+
+
+def _factor(B, Ct, sig, check=True):
+    """sig: (nb, 1, 1).  Returns (K, K^-1, K^-1 B, info) or None if any K is not positive definite.
+    ``check=False`` skips the host read of the factorisation status (the caller reads ``info`` later,
+    together with the residuals: a failed factor shows there before any result is accepted)."""
+    Kmat = sig * B - Ct
+    Lk, info = torch.linalg.cholesky_ex(Kmat)
+    if check and int(info.abs().max().item()) != 0:
+        return None
+    Li = _tri_inv_lower(Lk)
+    Kinv = Li.mT @ Li                           # two F^3 products (70 us each at F = 1000) buy 1 instead of 6
+    return Kmat, Kinv, Kinv @ B, info           # skinny products per cheap step, 4 per accurate one
+
+
+def _round_on_device(B, Ct, nrm, fac, X, sigma, pending_info, out, n_steps, first):
+    """``n_steps`` iterations X <- K^-1 B X, then Rayleigh-Ritz in span(X) and the residuals of the leading
+    ``out`` Ritz pairs -- all on the device, no host read.  ``first``: the first _ROUND0_CHEAP steps use the explicitly
+    formed K^-1 B (one skinny product; its rounding, eps cond(K), perturbs the operator of these steps only --
+    the accurate steps that follow converge to the eigenvectors of the true pencil) and the block is
+    re-orthogonalised after steps 4 and 8 (Cholesky QR: the noise directions shrink by (sigma - lambda_max) /
+    sigma per step, so 8 plain steps would leave it numerically rank deficient).  Accurate step:
+    K^-1 (B X) plus one step of iterative refinement against K itself.  Columns are rescaled every other step.
+    Returns (X, theta, hostvec) with hostvec = [worst relative residual | theta_0 | theta_out-1 | theta_b-1 |
+    sigma | pencil status | factorisation status]."""
+    Kmat, Kinv, KinvB = fac[0], fac[1], fac[2]
+    nb, b = X.shape[0], X.shape[-1]
+    for i in range(n_steps):
+        if first and i < _ROUND0_CHEAP:
+            X = KinvB @ X
+        else:
+            Z = B @ X
+            Y = Kinv @ Z
+            X = torch.baddbmm(Y, Kinv, torch.baddbmm(Z, Kmat, Y, alpha=-1.0))
+        if i & 1:
+            X = X / torch.linalg.norm(X, dim=-2, keepdim=True)
+        if first and i in (3, 7):
+            G = X.mT @ X
+            Lg, _ = torch.linalg.cholesky_ex(0.5 * (G + G.mT))
+            X = torch.linalg.solve_triangular(Lg.mT, X, upper=True, left=False)      # X <- X Lg^-T
+    # Rayleigh-Ritz in span(X):  (X^T Ct X) s = theta (X^T B X) s
+    BX = B @ X
+    CX = Ct @ X
+    Gb = X.mT @ BX
+    if X.is_cuda and b <= 32:
+        # the b x b pencil in one launch (Cholesky + Jacobi), its status rides on the round's host read
+        from . import ops
+        theta, S, bad = ops.gen_eig_small(X.mT @ CX, Gb)
+    else:
+        eye_b = torch.eye(b, dtype=B.dtype, device=B.device)
+        Lb, info_b = torch.linalg.cholesky_ex(0.5 * (Gb + Gb.mT))
+        Lbi = torch.linalg.solve_triangular(Lb, eye_b.expand(nb, b, b), upper=False)
+        Hs = Lbi @ (X.mT @ CX) @ Lbi.mT
+        theta, S = torch.linalg.eigh(0.5 * (Hs + Hs.mT))
+        theta = theta.flip(-1)
+        S = Lbi.mT @ S.flip(-1)
+        bad = info_b.abs().to(B.dtype).reshape(nb)
+    X = X @ S
+    res = torch.linalg.norm(CX @ S[..., :out] - (BX @ S[..., :out]) * theta[:, None, :out], dim=-2)
+    rel = res / (nrm * torch.linalg.norm(X[..., :out], dim=-2))
+    pend = (pending_info.abs().max().to(B.dtype).reshape(1) if pending_info is not None
+            else torch.zeros(1, dtype=B.dtype, device=B.device))
+    hostvec = torch.cat([rel.max().reshape(1), theta[:, 0], theta[:, out - 1], theta[:, b - 1],
+                         sigma.reshape(-1), bad.max().reshape(1), pend])
+    return X, theta, hostvec
+
+
+def _first_round_eager(B, Ct, out, b):
+    nb, F = B.shape[0], B.shape[-1]
+    nrm = torch.linalg.matrix_norm(Ct).unsqueeze(-1)         # (nb, 1) Frobenius norms, residual scale
+    sigma = torch.full((nb, 1, 1), 1.05, dtype=B.dtype, device=B.device)
+    # the first factorisation is used unchecked: its status rides on the round's host read
+    fac = _factor(B, Ct, sigma, check=False)
+    X0 = _start_block(F, b, B.device).expand(nb, F, b)
+    X, theta, hostvec = _round_on_device(B, Ct, nrm, fac, X0, sigma, fac[3], out, _ROUND0_STEPS, True)
+    return {"B": B, "Ct": Ct, "fac": fac, "X": X, "theta": theta, "sigma": sigma, "nrm": nrm, "host": hostvec}
+
+
+_ROUND0_GRAPHS = {}
+# Steps before the first Rayleigh-Ritz.  The explicitly formed K^-1 B carries a relative error ~ eps cond(K)
+# (1e-8 at C2), i.e. its eigenvectors are ~1e-5 off (gaps 2e-3): 4 cheap steps reach that floor (rate 0.06 per
+# step), more are wasted; each accurate step then gains a factor ~0.06, and the 1e-12 acceptance needs 7 of them
+# (measured at C2: 8 cheap + 5 accurate end at 1e-11, one round too many).
+_ROUND0_CHEAP = 4
+_ROUND0_STEPS = 11
+
+
+def _first_round(B, Ct, out, b):
+    """Round 0 of the shift-and-invert iteration; on CUDA a cached CUDA graph per (batch, F, out, device) whose
+    inputs are copied into static buffers (``DCG_EIG_GRAPH=0`` or a failed capture: eager).  The returned
+    tensors belong to the graph and are valid until its next replay (the caller clones what it returns)."""
+    if (not B.is_cuda or os.environ.get("DCG_EIG_GRAPH", "1") == "0" or torch.cuda.is_current_stream_capturing()):
+        return _first_round_eager(B, Ct, out, b)
+    key = (B.shape[0], B.shape[-1], out, b, B.device.index, B.dtype)
+    ent = _ROUND0_GRAPHS.get(key)
+    if ent is None:
+        ent = {"failed": False}
+        _ROUND0_GRAPHS[key] = ent
+        try:
+            Bs, Cs = B.clone().contiguous(), Ct.clone().contiguous()
+            side = torch.cuda.Stream(device=B.device)
+            side.wait_stream(torch.cuda.current_stream(B.device))
+            with torch.cuda.stream(side):
+                for _ in range(2):                         # library handles / workspaces before the capture
+                    _first_round_eager(Bs, Cs, out, b)
+            torch.cuda.current_stream(B.device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                outs = _first_round_eager(Bs, Cs, out, b)
+            ent.update(graph=graph, B=Bs, Ct=Cs, outs=outs)
+        except Exception:                                  # capture not possible here: stay eager
+            ent["failed"] = True
+            torch.cuda.synchronize(B.device)
+    if ent["failed"]:
+        return _first_round_eager(B, Ct, out, b)
+    ent["B"].copy_(B)
+    ent["Ct"].copy_(Ct)
+    ent["graph"].replay()
+    return ent["outs"]
 
 
 def _shift_invert_topk_native(B: torch.Tensor, Ct: torch.Tensor, out: int, tol: float = 1e-12, max_rounds: int = 10):

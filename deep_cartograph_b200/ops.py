@@ -639,6 +639,19 @@ def cluster_dispersion(Y: torch.Tensor, labels: torch.Tensor, means: torch.Tenso
 
 
 # ---- E1: F x F generalised eigenproblem (leading eigenpairs) ---------------------------------------
+def tri_inv_blocks_(L: torch.Tensor, out: torch.Tensor, nblk: int, bs: int) -> torch.Tensor:
+    """Inverses of the ``nblk`` diagonal blocks (``bs`` x ``bs``, at most 128) of the lower-triangular matrices
+    ``L`` (nb, F, F; any strides) into the same blocks of ``out`` (nb, F, F); the rest of ``out`` is left alone."""
+    _need_cuda("L", L, torch.float64)
+    _need_cuda("out", out, torch.float64)
+    if L.dim() != 3 or out.shape != L.shape or nblk * bs > L.shape[-1] or bs > 128:
+        raise ValueError("L, out: (nb, F, F) with nblk * bs <= F and bs <= 128")
+    _call(L.device, "dcg_tri_inv_blocks_f64", L.data_ptr(), out.data_ptr(), L.shape[0], nblk, bs,
+          L.stride(1), L.stride(2), L.stride(0), out.stride(1), out.stride(2), out.stride(0), _stream(L.device))
+    _count(1)
+    return out
+
+
 def eig_factor(B: torch.Tensor, Ct: torch.Tensor, sigma: float):
     """K = sigma B - Ct and the explicit inverse of its Cholesky factor, on the hand-written FP64 kernels
     (csrc/eig_dense.cu).  Returns (K, Li, LiT, status): K as formed (F x F), Li = chol(K)^-1 (lower),

@@ -283,6 +283,13 @@ int dcg_gen_eig_small_f64(const double* H, const double* G, int b, int batch,
  *                             other step, one Cholesky-QR after step `cholqr_at`, -1 for none), then
  *                             BX = B X, CX = Ct X (F x b) and the b x b Rayleigh-Ritz matrices
  *                             Gb = X^T B X, H = X^T Ct X.  One persistent cooperative kernel.          */
+/* Inverses of the `nblk` diagonal blocks (bs x bs, bs <= 128) of `batch` lower-triangular matrices, written to
+ * the same blocks of `out`; element (i, j) of matrix m at m * sbatch + i * srow + j * scol (any layout).  One CTA
+ * per block, forward substitution, no synchronisation (part of the explicit inverse of chol(K) in the
+ * shift-and-invert iteration that replaces mlcolvar's cholesky_eigh, cv_calculator.py:2257-2261).            */
+int dcg_tri_inv_blocks_f64(const double* L, double* out, int batch, int nblk, int bs,
+                           int64_t srow, int64_t scol, int64_t sbatch,
+                           int64_t orow, int64_t ocol, int64_t obatch, void* stream);
 int dcg_eig_shift_matrix_f64(const double* B, const double* Ct, int F, double sigma, double* K, double* K2,
                              void* stream);
 size_t dcg_eig_chol_inv_workspace_bytes(int F);
