@@ -34,7 +34,7 @@ sys.path.insert(0, ROOT)
 # committed `ncu --set full` captures under profiles/ (dram__bytes_read.sum + dram__bytes_write.sum).  A shape
 # without a capture reports null.
 TRAFFIC = {("tc_3xf16", 1_000_000, 1000): 11.88e9, ("tc_3xtf32", 1_000_000, 1000): 9.95e9,
-           ("tc_i8x3", 1_000_000, 1000): 4.866e9}
+           ("tc_i8x3", 1_000_000, 1000): 5.112e9}
 
 F = 1000
 N_PER_GPU = 1_000_000

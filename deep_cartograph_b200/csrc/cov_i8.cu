@@ -1239,7 +1239,7 @@ Layout8 layout8(int64_t n_rows, int f, int lag, int block) {
   L.n_sets = lag > 0 ? 2 : 1;
   L.fused = fused_applies(f, lag, block);
   L.ring = (int)std::min<int64_t>(std::max<int64_t>(env_i64("DCG_I8_RING", 4), 2), kMaxRing);
-  L.ring_budget = std::max<int64_t>(env_i64("DCG_I8_RING_BYTES", (int64_t)48 << 20), 1 << 20);
+  L.ring_budget = std::max<int64_t>(env_i64("DCG_I8_RING_BYTES", (int64_t)36 << 20), 1 << 20);
   L.wring = 0;
   if (L.fused) {
     L.wf = 0;
