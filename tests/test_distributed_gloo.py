@@ -61,6 +61,24 @@ def _worker(rank, world, port, n, f, lag, out):
         assert tot["M"] == rM == n - lag
         np.testing.assert_allclose(tot["S0"].numpy(), rS0, rtol=1e-11, atol=1e-8)
         np.testing.assert_allclose(tot["St"].numpy(), rSt, rtol=1e-11, atol=1e-8)
+        # the same with the sums laid out as ops.lagged_covariance lays them out -- one flat buffer
+        # [S0 | St | a | b | M], reduced in place -- and with a dict whose S0 no longer IS the slice of the
+        # buffer (replaced by the caller, e.g. re-standardised speculative sums): packed as before
+        flat = torch.cat([torch.from_numpy(S0).reshape(-1), torch.from_numpy(St).reshape(-1), torch.from_numpy(a),
+                          torch.from_numpy(b), torch.tensor([float(M)], dtype=torch.float64)])
+        views = {"S0": flat[:f * f].view(f, f), "St": flat[f * f:2 * f * f].view(f, f),
+                 "a": flat[2 * f * f:2 * f * f + f], "b": flat[2 * f * f + f:2 * f * f + 2 * f], "M": M, "flat": flat}
+        tot2 = shards.allreduce_sums(dict(views), m_total=n - lag)
+        assert tot2["S0"].data_ptr() == flat.data_ptr() and tot2["M"] == n - lag
+        for key in ("S0", "St", "a", "b"):
+            np.testing.assert_array_equal(tot2[key].numpy(), tot[key].numpy())
+        flat3 = torch.cat([torch.from_numpy(S0).reshape(-1), torch.from_numpy(St).reshape(-1), torch.from_numpy(a),
+                           torch.from_numpy(b), torch.tensor([float(M)], dtype=torch.float64)])
+        stale = {"S0": torch.from_numpy(S0).clone(), "St": flat3[f * f:2 * f * f].view(f, f),
+                 "a": flat3[2 * f * f:2 * f * f + f], "b": flat3[2 * f * f + f:2 * f * f + 2 * f], "M": M, "flat": flat3}
+        tot3 = shards.allreduce_sums(stale)
+        for key in ("S0", "St", "a", "b"):
+            np.testing.assert_array_equal(tot3[key].numpy(), tot[key].numpy())
         evals, V = linalg.tica_from_sums(tot["S0"], tot["St"], tot["a"], tot["b"], tot["M"], 3)
         revals, rV = oracle.tica(Z, lag, 3)
         np.testing.assert_allclose(evals.numpy(), revals, rtol=1e-9)
