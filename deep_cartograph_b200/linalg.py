@@ -245,6 +245,7 @@ def _first_round_eager(B, Ct, out, b):
 
 
 _ROUND0_GRAPHS = {}
+_ROUND0_GRAPHS_MAX = 8
 # Steps before the first Rayleigh-Ritz.  The explicitly formed K^-1 B carries a relative error ~ eps cond(K)
 # (1e-8 at C2), i.e. its eigenvectors are ~1e-5 off (gaps 2e-3): 4 cheap steps reach that floor (rate 0.06 per
 # step), more are wasted; each accurate step then gains a factor ~0.06, and the 1e-12 acceptance needs 7 of them
@@ -262,6 +263,8 @@ def _first_round(B, Ct, out, b):
     key = (B.shape[0], B.shape[-1], out, b, B.device.index, B.dtype)
     ent = _ROUND0_GRAPHS.get(key)
     if ent is None:
+        while len(_ROUND0_GRAPHS) >= _ROUND0_GRAPHS_MAX:          # each graph keeps ~15 F x F buffers alive
+            _ROUND0_GRAPHS.pop(next(iter(_ROUND0_GRAPHS)))
         ent = {"failed": False}
         _ROUND0_GRAPHS[key] = ent
         try:
